@@ -1,0 +1,231 @@
+/*
+ * dml_b200.h -- C ABI of libdml_b200.so: hand-written sm_100a CUDA kernels for the DMLNet
+ * per-pixel metric-learning hot path (distance head -> labels / EDS / MMSP scores -> exact
+ * AUROC / AUPR / FPR@95; DCE+VL loss forward/backward; per-class masked mean).
+ *
+ * The reference (Jun-CEN/Open-World-Semantic-Segmentation) is 100 % Python and has no FFI;
+ * this header is what a ctypes binding of its operator surface binds.  Each entry point
+ * cites the reference lines it replaces (paths relative to the reference root).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in `_host`;
+ *   - tensors are dense, row-major, in the stated layout; fp32 unless stated;
+ *   - the library never allocates: callers pass outputs and workspaces
+ *     (`*_workspace_bytes` tells how much);
+ *   - kernels are enqueued on `stream` (a cudaStream_t) of the CURRENT device and the
+ *     call returns without synchronising; no global mutable state => re-entrant from
+ *     one host thread per GPU (nn.DataParallel's threading model);
+ *   - return value: DML_OK (0) or a negative DML_ERR_* code; `dml_error_string` decodes.
+ */
+#ifndef DML_B200_H_
+#define DML_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DML_B200_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define DML_API __attribute__((visibility("default")))
+#else
+#define DML_API
+#endif
+
+typedef void* dml_stream_t; /* cudaStream_t */
+
+enum {
+  DML_OK = 0,
+  DML_ERR_INVALID_ARG = -1,   /* bad shape / null pointer / unsupported combination */
+  DML_ERR_UNSUPPORTED_DIM = -2, /* embedding dim or class count outside the compiled range */
+  DML_ERR_CUDA = -3,          /* a CUDA runtime call failed (see dml_last_cuda_error) */
+  DML_ERR_WORKSPACE = -4      /* workspace too small */
+};
+
+DML_API int dml_abi_version(void);
+DML_API const char* dml_error_string(int code);
+/* cudaError_t of the most recent failed runtime call made by this thread's entry point. */
+DML_API int dml_last_cuda_error(void);
+/* Largest supported embedding dim D and class count K (compile-time unrolled kernels). */
+DML_API int dml_max_dim(void);
+
+/* ------------------------------------------------------------------------------------ *
+ * (a) Fused distance + score head.
+ *
+ * Replaces, in one pass over the NCHW embedding:
+ *   anomaly/models/models.py:636-657                (distance logits, prototypes :614-618)
+ *   DeepLabV3Plus-Pytorch/network/utils.py:89-118   (same, full resolution, NHWC `features`)
+ *   anomaly/eval_ood_traditional.py:218             (argmax label)
+ *   anomaly/eval_ood_traditional.py:276-278,288-290 (msp, maxlogit)
+ *   anomaly/eval_ood_traditional.py:301-304         (EDS raw sum + clamp; :305 normalise is
+ *                                                    dml_scores_finalize / fused key-gen)
+ *   anomaly/eval_ood_traditional.py:434             (max-softmax for MMSP)
+ *   DeepLabV3Plus-Pytorch/test_embedding.py:339-350 (argmax, max-softmax, dis_sum + clamp)
+ *   DeepLabV3Plus-Pytorch/test_embedding.py:428-433,445 (NPM novel-prototype override, fp64)
+ *   DeepLabV3Plus-Pytorch/metrics/stream_metrics.py:49-55, anomaly/utils.py:128-156
+ *                                                   (confusion counts, when `gt` is given)
+ *
+ *   z[b,k,p] = - sum_d (x[b,d,p] - mu[k,d])^2
+ * Prototypes: `mu == NULL` => mu = diag_m * I_K (requires K == D; the only case the
+ * reference ships) computed with a cancellation-free leave-one-out sum of squares;
+ * otherwise `mu` is a dense [K,D] table (direct form).
+ * Every output pointer may be NULL (not produced).
+ * ------------------------------------------------------------------------------------ */
+typedef struct dml_head_params {
+  uint32_t struct_bytes;      /* sizeof(dml_head_params), ABI guard */
+  int32_t B, D, K, H, W;      /* x is [B,D,H,W] */
+  const float* x;
+  const float* mu;            /* [K,D] or NULL */
+  float diag_m;               /* prototype magnitude when mu == NULL (reference: 3) */
+  int32_t input_is_logits;    /* != 0: x already holds the logits z [B,K,H,W] (anomaly path, where the
+                                 distances are taken at stride 8 and upsampled/averaged first,
+                                 anomaly/eval_ood_traditional.py:198-210); scores only, K == D */
+  int32_t score_first_class;  /* 0, or 1 for OOD.exclude_back (scores skip channel 0;
+                                 labels/logits still use all classes) */
+  float eds_clamp;            /* > 0: eds = min(eds, clamp) (400 anomaly / 1000 DeepLab); <= 0: none */
+
+  /* NPM novel prototypes (optional): [n_novel, D] float64, override label where
+     z_nov > novel_thr && z_nov > max_k z_k; label written = novel_label_base + j. */
+  const double* mu_novel;
+  int32_t n_novel;
+  int32_t novel_label_base;
+  double novel_thr;
+
+  /* outputs */
+  float* logits;              /* [B,K,H,W] */
+  uint8_t* label_u8;          /* [B,H,W] argmax_k z (first max), after NPM override */
+  int64_t* label_i64;         /* same as int64 (torch.max parity) */
+  float* maxlogit;            /* [B,H,W] max_k z over score classes */
+  float* eds;                 /* [B,H,W] -sum_k z over score classes, clamped */
+  float* msp;                 /* [B,H,W] max_k softmax_k(z) over score classes */
+  float* features_nhwc;       /* [B,H,W,D] contiguous copy of x (DeepLab return value) */
+  double* novel_dist;         /* [n_novel,B,H,W] z_nov (float64) */
+  float* minmax;              /* [B,4] per image (eds_min, eds_max, msp_min, msp_max); needs eds/msp
+                                 to be computed (their map pointers may still be NULL) */
+  int32_t want_eds_minmax, want_msp_minmax;
+
+  /* fused confusion counts (optional) */
+  const uint8_t* gt_u8;       /* [B,H,W] ground truth; or */
+  const int64_t* gt_i64;      /* [B,H,W] */
+  unsigned long long* confusion; /* [conf_rows, conf_cols] += count; gt outside [0,conf_rows) ignored */
+  int32_t conf_rows, conf_cols;
+} dml_head_params;
+
+DML_API int dml_head_forward(const dml_head_params* p, dml_stream_t stream);
+
+/* Per-image min-max normalise + mix (anomaly/eval_ood_traditional.py:101-106,305,435,447-448):
+ *   eds_n = (eds - min)/(max - min), msp_n likewise, c = 1/(1+exp(lambda (eds_n - thr))),
+ *   mix = c*eds_n + (1-c)*msp_n.  In-place allowed (out == in).  Outputs may be NULL.
+ * `complement` != 0 writes 1 - eds_n instead (DeepLabV3Plus-Pytorch/test_embedding.py:370). */
+DML_API int dml_scores_finalize(const float* eds, const float* msp, const float* minmax /*[B,4]*/,
+                        int32_t B, int64_t pixels_per_image, float lambda, float thr, int32_t complement,
+                        float* eds_norm, float* msp_norm, float* mix, dml_stream_t stream);
+
+/* Confusion counts on their own (stream_metrics.py:49-55; anomaly/utils.py:128-156):
+ * confusion[gt*cols + pred] += 1 for gt in [0,rows).  Exactly one of gt_u8/gt_i64 and one of
+ * pred_u8/pred_i64 is non-NULL. */
+DML_API int dml_confusion(const uint8_t* gt_u8, const int64_t* gt_i64, const uint8_t* pred_u8,
+                  const int64_t* pred_i64, int64_t n, int32_t rows, int32_t cols,
+                  unsigned long long* confusion, dml_stream_t stream);
+
+/* PLM merge (DeepLabV3Plus-Pytorch/test_self_distillation.py:292-297):
+ * base[p] = novel_label where head[p] == novel_label. */
+DML_API int dml_plm_merge(uint8_t* base_u8, int64_t* base_i64, const uint8_t* head_u8, const int64_t* head_i64,
+                  int64_t n, int32_t novel_label, dml_stream_t stream);
+
+/* ------------------------------------------------------------------------------------ *
+ * (b) Fused DCE + VL (+ Inter) loss, forward and backward, straight from the embedding.
+ *   anomaly/models/models.py:42-78 (CE + alpha*VL, ignore -1)
+ *   DeepLabV3Plus-Pytorch/utils/loss.py:34-82 (line 79 form; shipped early return = alpha=beta=0)
+ *   loss = (CE + alpha*VL + beta*Inter)/n  -- see SURVEY.md appendix A.6.
+ * Forward writes 4 doubles: loss, CE, VL, Inter and the valid-pixel count as double in [4].
+ * `partials` is a workspace of dml_loss_workspace_bytes(B,H,W).
+ * Backward recomputes the distances and writes dL/dx [B,D,H,W] scaled by *grad_out (device scalar).
+ * ------------------------------------------------------------------------------------ */
+DML_API size_t dml_loss_workspace_bytes(int32_t B, int32_t H, int32_t W);
+DML_API int dml_loss_forward(const float* x, const float* mu, float diag_m, const uint8_t* target_u8,
+                     const int64_t* target_i64, int64_t ignore_index, int32_t B, int32_t D, int32_t K,
+                     int32_t H, int32_t W, double alpha, double beta, void* partials,
+                     double* out5, dml_stream_t stream);
+DML_API int dml_loss_backward(const float* x, const float* mu, float diag_m, const uint8_t* target_u8,
+                      const int64_t* target_i64, int64_t ignore_index, int32_t B, int32_t D, int32_t K,
+                      int32_t H, int32_t W, double alpha, double beta, const double* out5,
+                      const float* grad_out, float* dx, dml_stream_t stream);
+
+/* ------------------------------------------------------------------------------------ *
+ * (c) Masked per-class mean (few-shot novel prototype generation).
+ *   DeepLabV3Plus-Pytorch/test_embedding.py:413-419, utils/loss.py:65-67
+ * sums[b,c,:] = sum_{p: label[b,p]==c} x[b,:,p] (float64), counts[b,c] = #pixels.
+ * x is NCHW (`nhwc`=0) or NHWC (`nhwc`=1).  Labels outside [0,n_cls) are skipped.
+ * ------------------------------------------------------------------------------------ */
+DML_API size_t dml_class_sums_workspace_bytes(int32_t B, int32_t D, int32_t n_cls, int64_t pixels_per_image);
+DML_API int dml_class_sums(const float* x, int32_t nhwc, const uint8_t* label_u8, const int64_t* label_i64,
+                   int32_t B, int32_t D, int64_t pixels_per_image, int32_t n_cls, void* workspace,
+                   double* sums /*[B,n_cls,D]*/, long long* counts /*[B,n_cls]*/, dml_stream_t stream);
+
+/* ------------------------------------------------------------------------------------ *
+ * (d) Exact, tie-aware ranking metrics (AUROC, AUPR, FPR@recall) on the GPU.
+ *   anomaly/anom_utils.py:25-65 (fpr_and_fdr_at_recall), :67-78 (get_measures -> sklearn
+ *   roc_auc_score / average_precision_score), :95-116; anomaly/eval_ood_traditional.py:128-148.
+ *
+ * Pipeline: key generation (order-preserving u32 key of the score, positive flag packed
+ * in bit 0) -> LSD radix sort (8-bit digits, decoupled look-back) per segment -> segmented
+ * scan over distinct-score groups -> AUROC / AP / FPR reductions.  Segments are
+ * independent (one per image for the reference's per-image semantics, one for pooled).
+ * ------------------------------------------------------------------------------------ */
+typedef struct dml_ood_result {
+  double auroc, aupr, fpr;    /* NaN when the segment has a single class */
+  long long n_pos, n_neg;
+  long long n_nan;            /* NaN scores seen (Python raises ValueError like sklearn) */
+  long long n_groups;         /* distinct score values */
+} dml_ood_result;
+
+/* Statistics of the order-preserving ("sortable") u32 image of the ranking key, used to choose
+ * `key_base` for arbitrary scores: seg_stats (device, [n_seg,4] int64) = (min, max, n_nan, 0). */
+DML_API int dml_ood_keystats(const float* values, int32_t score_kind, int32_t n_seg, int64_t seg_len,
+                     long long* seg_stats, dml_stream_t stream);
+
+/* Key generation.  score_kind: 0 = `conf` map, ranked as score = -conf (positives expected
+ * at LOW conf; anomaly/eval_ood_traditional.py:139-141); 1 = plain score (higher = positive).
+ * If `minmax` != NULL the kernel first applies the per-segment normalisation
+ * (v - min)/(max - min) with min/max = minmax[seg*4 + minmax_slot*2 + {0,1}] in fp32, exactly as
+ * NumPy does (fusing eval_ood_traditional.py:305 into key-gen), and optionally stores it to
+ * `conf_out`.  Positives: gt label in `out_label_mask` (bit l set for label l, labels 0..63;
+ * exactly one of gt_u8 / gt_i64 / pos_u8 is non-NULL; pos_u8 != 0 marks positives directly).
+ * Packed key = ((sortable(key) - key_base) << 1) | positive; all keys of a call must lie in
+ * [key_base, key_base + 2^31) -- true with key_base = 0x80000000 for any non-negative conf
+ * (e.g. normalised maps in [0,1]); violations are counted, not silently wrapped.
+ * seg_stats (device, [n_seg,4] int64) = (n_pos, n_nan, n_out_of_window, 0). */
+DML_API int dml_ood_keygen(const float* values, const float* minmax, int32_t minmax_slot, float* conf_out,
+                   const uint8_t* gt_u8, const int64_t* gt_i64, uint64_t out_label_mask,
+                   const uint8_t* pos_u8, int32_t score_kind, uint32_t key_base, int32_t n_seg,
+                   int64_t seg_len, uint32_t* keys, long long* seg_stats, dml_stream_t stream);
+
+DML_API size_t dml_ood_workspace_bytes(int32_t n_seg, int64_t seg_len);
+/* Sort `keys` (n_seg segments of seg_len packed keys; clobbered) and evaluate every segment.
+ * `seg_stats` is dml_ood_keygen's output (n_pos / n_nan per segment, device).
+ * `results` is a DEVICE array of n_seg dml_ood_result.  recall_level: 0.95 in the reference. */
+DML_API int dml_ood_eval_segments(uint32_t* keys, const long long* seg_stats, int32_t n_seg, int64_t seg_len,
+                          double recall_level, void* workspace, size_t workspace_bytes,
+                          dml_ood_result* results, dml_stream_t stream);
+
+/* Building blocks for the multi-GPU pooled metric (locally sorted shards + NCCL exchange on the
+ * Python side).  dml_ood_sort: radix sort only, bits [begin_bit, end_bit); `*sorted_out` (host
+ * pointer-to-pointer) receives the device buffer holding the result (keys, or inside workspace).
+ * dml_ood_scan_range: group scan over an already sorted key range that starts on a score-group
+ * boundary.  range_info (device, 4 int64) = (pos_before, idx_before, total_pos, total_n) of the
+ * global ranking.  partial_out (device, 48 bytes) = { u64 auroc_num; f64 ap_sum; f64 best_dist;
+ * i64 best_idx; i64 best_fps; i64 n_groups } -- ranges combine by (+, +, argmin(dist, -idx), +). */
+DML_API int dml_ood_sort(uint32_t* keys, int32_t n_seg, int64_t seg_len, int32_t begin_bit, int32_t end_bit,
+                 void* workspace, size_t workspace_bytes, uint32_t** sorted_out, dml_stream_t stream);
+DML_API int dml_ood_scan_range(const uint32_t* sorted_keys, int64_t n, const long long* range_info,
+                       double recall_level, void* workspace, size_t workspace_bytes, void* partial_out,
+                       dml_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DML_B200_H_ */

@@ -1,0 +1,154 @@
+// C-ABI entry points of the loss (b) and class-sum (c) paths.  Kernels: dml_loss.cuh, dml_reduce.cuh.
+#include "dml_loss.cuh"
+#include "dml_reduce.cuh"
+
+namespace dml {
+namespace {
+
+int loss_grid_x(long long hw, int vec) {
+  long long gx = (hw + (long long)LOSS_THREADS * vec - 1) / ((long long)LOSS_THREADS * vec);
+  if (gx > LOSS_MAX_BLOCKS_X) gx = LOSS_MAX_BLOCKS_X;
+  return gx < 1 ? 1 : (int)gx;
+}
+
+// fixed-order reduction of the per-block partials -> (loss, CE, VL, Inter, n_valid)
+__global__ void __launch_bounds__(256) loss_finalize_kernel(const double* __restrict__ partials, int n_blocks, int B,
+                                                            long long hw, double alpha, double beta, double* out5) {
+  __shared__ double s_r[4][256];
+  const int tid = threadIdx.x;
+  const int per = (n_blocks + 255) / 256;
+  const int b0 = tid * per;
+  int b1 = b0 + per;
+  if (b1 > n_blocks) b1 = n_blocks;
+  double r[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int i = b0; i < b1; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) r[j] += partials[(size_t)i * 4 + j];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) s_r[j][tid] = r[j];
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (tid < o)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) s_r[j][tid] += s_r[j][tid + o];
+    __syncthreads();
+  }
+  if (tid == 0) {
+    const double nv = s_r[3][0];
+    const double ce = s_r[0][0] / nv;  // mean over valid pixels (NaN when there is none, like torch)
+    const double vl = s_r[1][0] / (double)hw;
+    const double in = s_r[2][0] / (double)hw;
+    out5[0] = (ce + alpha * vl + beta * in) / (double)B;
+    out5[1] = ce;
+    out5[2] = vl;
+    out5[3] = in;
+    out5[4] = nv;
+  }
+}
+
+int reduce_grid_x(long long hw) {
+  long long gx = (hw + RED_THREADS * 8 - 1) / (RED_THREADS * 8);
+  if (gx > 64) gx = 64;
+  return gx < 1 ? 1 : (int)gx;
+}
+
+// sums[b,c,d] = sum over blocks (fixed order); counts likewise
+__global__ void __launch_bounds__(256) class_sums_finalize_kernel(const double* __restrict__ partials, int gx, int n_cls,
+                                                                  int D, double* sums, long long* counts) {
+  const int b = blockIdx.y;
+  const int row = D + 1;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // over n_cls * row
+  if (i >= n_cls * row) return;
+  double t = 0.0;
+  for (int g = 0; g < gx; ++g) t += partials[((size_t)b * gx + g) * n_cls * row + i];
+  const int c = i / row, d = i - c * row;
+  if (d < D) sums[((size_t)b * n_cls + c) * D + d] = t;
+  else counts[(size_t)b * n_cls + c] = (long long)(t + 0.5);
+}
+
+int loss_common(bool bwd, const float* x, const float* mu, float diag_m, const uint8_t* t_u8, const int64_t* t_i64,
+                int64_t ignore_index, int B, int D, int K, int H, int W, double alpha, double beta, void* partials,
+                double* out5, const float* grad_out, float* dx, cudaStream_t stream) {
+  if (!x || (!t_u8 == !t_i64) || B < 1 || D < 1 || K < 1 || H < 1 || W < 1 || !out5) return DML_ERR_INVALID_ARG;
+  if (D > DML_MAX_DIM || K > DML_MAX_DIM) return DML_ERR_UNSUPPORTED_DIM;
+  if (B > 65535) return DML_ERR_INVALID_ARG;
+  const bool ident = mu == nullptr;
+  if (ident && K != D) return DML_ERR_INVALID_ARG;
+  if (bwd ? (!grad_out || !dx) : !partials) return DML_ERR_INVALID_ARG;
+  const long long hw = (long long)H * W;
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  int vec = (ident && hw % 4 == 0 && al16(x) && (!bwd || al16(dx))) ? 4 : 1;
+  if (D > 24) vec = 1;
+  LossArgs a;
+  a.x = x; a.mu = mu; a.diag_m = diag_m; a.t_u8 = t_u8; a.t_i64 = (const long long*)t_i64; a.ignore = ignore_index;
+  a.B = B; a.K = K; a.HW = hw; a.alpha = alpha; a.beta = beta;
+  a.partials = reinterpret_cast<double*>(partials); a.out5 = out5; a.grad_out = grad_out; a.dx = dx;
+  const int gx = loss_grid_x(hw, vec);
+  int rc;
+  if (D <= 8) rc = loss_dispatch_1_8(D, ident, vec, bwd, a, gx, stream);
+  else if (D <= 16) rc = loss_dispatch_9_16(D, ident, vec, bwd, a, gx, stream);
+  else if (D <= 24) rc = loss_dispatch_17_24(D, ident, vec, bwd, a, gx, stream);
+  else rc = loss_dispatch_25_32(D, ident, vec, bwd, a, gx, stream);
+  if (rc != DML_OK || bwd) return rc;
+  loss_finalize_kernel<<<1, 256, 0, stream>>>(a.partials, gx * B, B, hw, alpha, beta, out5);
+  DML_LAUNCH_CHECK();
+  return DML_OK;
+}
+
+}  // namespace
+}  // namespace dml
+
+using namespace dml;
+
+extern "C" {
+#pragma GCC visibility push(default)
+
+size_t dml_loss_workspace_bytes(int32_t B, int32_t H, int32_t W) {
+  if (B < 1 || H < 1 || W < 1) return 256;
+  // vec = 1 gives the largest grid
+  return (size_t)B * loss_grid_x((long long)H * W, 1) * 4 * sizeof(double);
+}
+
+int dml_loss_forward(const float* x, const float* mu, float diag_m, const uint8_t* target_u8, const int64_t* target_i64,
+                     int64_t ignore_index, int32_t B, int32_t D, int32_t K, int32_t H, int32_t W, double alpha, double beta,
+                     void* partials, double* out5, dml_stream_t stream) {
+  return loss_common(false, x, mu, diag_m, target_u8, target_i64, ignore_index, B, D, K, H, W, alpha, beta, partials, out5,
+                     nullptr, nullptr, (cudaStream_t)stream);
+}
+
+int dml_loss_backward(const float* x, const float* mu, float diag_m, const uint8_t* target_u8, const int64_t* target_i64,
+                      int64_t ignore_index, int32_t B, int32_t D, int32_t K, int32_t H, int32_t W, double alpha, double beta,
+                      const double* out5, const float* grad_out, float* dx, dml_stream_t stream) {
+  return loss_common(true, x, mu, diag_m, target_u8, target_i64, ignore_index, B, D, K, H, W, alpha, beta, nullptr,
+                     const_cast<double*>(out5), grad_out, dx, (cudaStream_t)stream);
+}
+
+size_t dml_class_sums_workspace_bytes(int32_t B, int32_t D, int32_t n_cls, int64_t pixels_per_image) {
+  if (B < 1 || D < 1 || n_cls < 1 || pixels_per_image < 1) return 256;
+  return (size_t)B * reduce_grid_x(pixels_per_image) * n_cls * (D + 1) * sizeof(double);
+}
+
+int dml_class_sums(const float* x, int32_t nhwc, const uint8_t* label_u8, const int64_t* label_i64, int32_t B, int32_t D,
+                   int64_t hw, int32_t n_cls, void* workspace, double* sums, long long* counts, dml_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!x || (!label_u8 == !label_i64) || !workspace || !sums || !counts) return DML_ERR_INVALID_ARG;
+  if (B < 1 || D < 1 || n_cls < 1 || hw < 1 || B > 65535) return DML_ERR_INVALID_ARG;
+  if (D > DML_MAX_DIM || n_cls > 64) return DML_ERR_UNSUPPORTED_DIM;
+  ReduceArgs a;
+  a.x = x; a.nhwc = nhwc; a.l_u8 = label_u8; a.l_i64 = (const long long*)label_i64;
+  a.B = B; a.n_cls = n_cls; a.HW = hw; a.partials = reinterpret_cast<double*>(workspace);
+  const int gx = reduce_grid_x(hw);
+  int rc;
+  if (D <= 8) rc = reduce_dispatch_1_8(D, a, gx, stream);
+  else if (D <= 16) rc = reduce_dispatch_9_16(D, a, gx, stream);
+  else if (D <= 24) rc = reduce_dispatch_17_24(D, a, gx, stream);
+  else rc = reduce_dispatch_25_32(D, a, gx, stream);
+  if (rc != DML_OK) return rc;
+  const int n = n_cls * (D + 1);
+  class_sums_finalize_kernel<<<dim3((unsigned)ceil_div_i(n, 256), (unsigned)B), 256, 0, stream>>>(a.partials, gx, n_cls, D, sums, counts);
+  DML_LAUNCH_CHECK();
+  return DML_OK;
+}
+
+#pragma GCC visibility pop
+}  // extern "C"

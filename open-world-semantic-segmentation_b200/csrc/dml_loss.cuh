@@ -1,0 +1,240 @@
+// Fused DCE + VL (+ Inter) loss straight from the embedding, forward and backward
+// (north-star kernel (b)).
+//
+// Replaces anomaly/models/models.py:42-78 (CE + alpha*VL with the per-(image,class) host loop) and
+// DeepLabV3Plus-Pytorch/utils/loss.py:34-82 (line-79 form; the shipped early return is alpha=beta=0).
+//
+//   z_k   = -||x - mu_k||^2
+//   CE_p  = logsumexp_k z_k - z_y           (valid pixels: target != ignore_index)
+//   VL_p  = -z_y = d_y,   Inter_p = sum_{k != y} z_k
+//   loss  = (mean_valid CE + alpha * sum_i VL_i / T + beta * sum_i Inter_i / T) / n,  T = H*W
+//   dL/dz_k = (1/n) [ (softmax_k - [k=y]) / N_valid - alpha/T [k=y] + beta/T [k!=y] ]
+//   dL/dx_d = -2 [ (sum_k g_k) x_d - sum_k g_k mu_kd ]
+//
+// With mu = m I the softmax over z equals the softmax over 2 m x_k (z_k - z_j = 2m(x_k - x_j)
+// exactly), which is what the kernel evaluates: no cancellation, no K x D work.
+// Reductions are deterministic: per-block double partials + fixed-order finalize.
+#pragma once
+#include "dml_common.cuh"
+
+namespace dml {
+
+constexpr int LOSS_THREADS = 256;
+constexpr int LOSS_MAX_BLOCKS_X = 4096;
+
+struct LossArgs {
+  const float* x;
+  const float* mu;     // dense [K,D] or nullptr
+  float diag_m;
+  const uint8_t* t_u8;
+  const long long* t_i64;
+  long long ignore;
+  int B, K;
+  long long HW;
+  double alpha, beta;
+  double* partials;    // [B * gridDim.x][4] : ce, vl, inter, n_valid
+  const double* out5;  // backward: forward results (n_valid at [4])
+  const float* grad_out;
+  float* dx;
+};
+
+template <int D, bool IDENT, int VEC, bool BWD>
+__global__ void __launch_bounds__(LOSS_THREADS) loss_kernel(const LossArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_dyn[];
+  float* s_mu = reinterpret_cast<float*>(smem_dyn);  // dense only: [K][D]
+  const int K = IDENT ? D : a.K;
+  if constexpr (!IDENT) {
+    for (int i = threadIdx.x; i < K * D; i += LOSS_THREADS) s_mu[i] = a.mu[i];
+    __syncthreads();
+  }
+  const int b = blockIdx.y;
+  const uint64_t pol = policy_evict_first();
+  const float two_m = 2.0f * a.diag_m;
+  constexpr float LOG2E = 1.4426950408889634f;
+
+  double ce_acc = 0.0, vl_acc = 0.0, in_acc = 0.0;
+  unsigned nv_acc = 0;
+
+  // backward constants
+  float gscale = 0.f, inv_nv = 0.f, a_t = 0.f, b_t = 0.f;
+  if constexpr (BWD) {
+    gscale = a.grad_out[0] / (float)a.B;
+    inv_nv = (float)(1.0 / a.out5[4]);
+    a_t = (float)(a.alpha / (double)a.HW);
+    b_t = (float)(a.beta / (double)a.HW);
+  }
+
+  const long long per_iter = (long long)gridDim.x * LOSS_THREADS * VEC;
+  for (long long p0 = ((long long)blockIdx.x * LOSS_THREADS + threadIdx.x) * VEC; p0 < a.HW; p0 += per_iter) {
+    float x[D][VEC];
+    const float* xb = a.x + ((long long)b * D) * a.HW + p0;
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      const FVec<VEC> t = ld_stream<VEC>(xb + (long long)d * a.HW, pol);
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) x[d][v] = t.v[v];
+    }
+    const long long pix = (long long)b * a.HW + p0;
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      const long long tgt = a.t_u8 ? (long long)a.t_u8[pix + v] : a.t_i64[pix + v];
+      const bool valid = (tgt != a.ignore) && tgt >= 0 && tgt < K;
+      const int y = valid ? (int)tgt : 0;
+
+      // u_k = z_k - z_ext (<= 0), with z_ext the largest logit.  mu = m I: u_k = 2m (x_k - x_ext) from the
+      // exact difference of embeddings (x_ext = max x for m > 0, min x for m < 0); dense: from the distances.
+      float zk[IDENT ? 1 : DML_MAX_DIM];  // dense: logits kept for the second sweep
+      float ext = 0.f, dy = 0.f, dsum = 0.f;
+      int kext = 0;
+      if constexpr (IDENT) {
+        ext = x[0][v];
+#pragma unroll
+        for (int k = 1; k < D; ++k) {
+          const bool better = two_m >= 0.f ? (x[k][v] > ext) : (x[k][v] < ext);
+          if (better) { ext = x[k][v]; kext = k; }
+        }
+      } else {
+        ext = __int_as_float(0xff800000);
+#pragma unroll
+        for (int k = 0; k < DML_MAX_DIM; ++k) {
+          if (k < K) {
+            float acc = 0.f;
+#pragma unroll
+            for (int d = 0; d < D; ++d) {
+              const float t = x[d][v] - s_mu[k * D + d];
+              acc = fmaf(t, t, acc);
+            }
+            zk[k] = -acc;
+            if (-acc > ext) { ext = -acc; kext = k; }
+            if (k == y) dy = acc;
+            dsum += acc;
+          }
+        }
+      }
+      // r = sum_{k != kext} exp(u_k); the extremal term is exactly 1 and is kept out of the sum so that
+      // log1p(r) stays accurate for well-separated pixels.  uy = u_y.
+      float r = 0.f, uy = 0.f;
+      if constexpr (IDENT) {
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+          const float u = two_m * (x[k][v] - ext);
+          if (k == y) uy = u;
+          if (k != kext) r += ex2_approx(u * LOG2E);
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < DML_MAX_DIM; ++k)
+          if (k < K) {
+            const float u = zk[k] - ext;
+            if (k == y) uy = u;
+            if (k != kext) r += ex2_approx(u * LOG2E);
+          }
+      }
+      if constexpr (!BWD) {
+        if (valid) {
+          if constexpr (IDENT) {
+            // d_y = sum_{d != y} x_d^2 + (x_y - m)^2 (positive terms only);
+            // sum_k d_k = K ||x||^2 - 2m sum_k x_k + K m^2 (large, only feeds Inter)
+            float xy = 0.f, loo = 0.f, sx = 0.f, sumsq = 0.f;
+#pragma unroll
+            for (int k = 0; k < D; ++k) {
+              if (k == y) xy = x[k][v]; else loo = fmaf(x[k][v], x[k][v], loo);
+              sumsq = fmaf(x[k][v], x[k][v], sumsq);
+              sx += x[k][v];
+            }
+            const float ty_m = xy - a.diag_m;
+            dy = fmaf(ty_m, ty_m, loo);
+            dsum = (float)D * sumsq - two_m * sx + (float)D * a.diag_m * a.diag_m;
+          }
+          const float ce = log1pf(r) - uy;  // logsumexp_k z_k - z_y
+          ce_acc += (double)ce;
+          vl_acc += (double)dy;
+          in_acc += (double)(-(dsum - dy));
+          ++nv_acc;
+        }
+      } else {
+        // g_k = gscale * [ (p_k - [k=y]) / Nv - a_t [k=y] + b_t [k!=y] ]  (valid pixels only)
+        const float inv_s = 1.0f / (1.0f + r);
+        const float G = gscale * (-a_t + b_t * (float)(K - 1));  // sum_k g_k (softmax sums to 1)
+        if constexpr (IDENT) {
+#pragma unroll
+          for (int d = 0; d < D; ++d) {
+            const float pk = (d == kext ? 1.0f : ex2_approx(two_m * (x[d][v] - ext) * LOG2E)) * inv_s;
+            const float oh = (d == y) ? 1.f : 0.f;
+            const float gk = gscale * ((pk - oh) * inv_nv - a_t * oh + b_t * (1.f - oh));
+            const float g = -2.0f * (G * x[d][v] - a.diag_m * gk);
+            x[d][v] = valid ? g : 0.f;
+          }
+        } else {
+          float gx[D];
+#pragma unroll
+          for (int d = 0; d < D; ++d) gx[d] = G * x[d][v];
+#pragma unroll
+          for (int k = 0; k < DML_MAX_DIM; ++k) {
+            if (k < K) {
+              const float pk = (k == kext ? 1.0f : ex2_approx((zk[k] - ext) * LOG2E)) * inv_s;
+              const float oh = (k == y) ? 1.f : 0.f;
+              const float gk = gscale * ((pk - oh) * inv_nv - a_t * oh + b_t * (1.f - oh));
+#pragma unroll
+              for (int d = 0; d < D; ++d) gx[d] = fmaf(-gk, s_mu[k * D + d], gx[d]);
+            }
+          }
+#pragma unroll
+          for (int d = 0; d < D; ++d) x[d][v] = valid ? -2.0f * gx[d] : 0.f;
+        }
+      }
+    }
+    if constexpr (BWD) {
+      float* db = a.dx + ((long long)b * D) * a.HW + p0;
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        FVec<VEC> t;
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) t.v[v] = x[d][v];
+        st_stream<VEC>(db + (long long)d * a.HW, t);
+      }
+    }
+  }
+
+  if constexpr (!BWD) {
+    __shared__ double s_r[4][LOSS_THREADS / 32];
+    double r[4] = {ce_acc, vl_acc, in_acc, (double)nv_acc};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      r[j] = warp_reduce_sum_d(r[j]);
+      if ((threadIdx.x & 31) == 0) s_r[j][threadIdx.x >> 5] = r[j];
+    }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+      double t = 0.0;
+#pragma unroll
+      for (int i = 0; i < LOSS_THREADS / 32; ++i) t += s_r[threadIdx.x][i];
+      a.partials[((size_t)b * gridDim.x + blockIdx.x) * 4 + threadIdx.x] = t;
+    }
+  }
+}
+
+template <int D, bool IDENT, int VEC, bool BWD>
+int launch_loss(const LossArgs& a, int grid_x, cudaStream_t stream) {
+  dim3 grid((unsigned)grid_x, (unsigned)a.B);
+  const size_t smem = IDENT ? 0 : (size_t)a.K * D * sizeof(float);
+  loss_kernel<D, IDENT, VEC, BWD><<<grid, LOSS_THREADS, smem, stream>>>(a);
+  DML_LAUNCH_CHECK();
+  return DML_OK;
+}
+
+#define DML_LOSS_CASE(Dv)                                                                                     \
+  case Dv:                                                                                                    \
+    if (ident) {                                                                                              \
+      if (bwd) return vec == 4 ? launch_loss<Dv, true, 4, true>(a, gx, s) : launch_loss<Dv, true, 1, true>(a, gx, s);   \
+      return vec == 4 ? launch_loss<Dv, true, 4, false>(a, gx, s) : launch_loss<Dv, true, 1, false>(a, gx, s);          \
+    }                                                                                                         \
+    if (bwd) return launch_loss<Dv, false, 1, true>(a, gx, s);                                                \
+    return launch_loss<Dv, false, 1, false>(a, gx, s);
+
+int loss_dispatch_1_8(int D, bool ident, int vec, bool bwd, const LossArgs& a, int gx, cudaStream_t s);
+int loss_dispatch_9_16(int D, bool ident, int vec, bool bwd, const LossArgs& a, int gx, cudaStream_t s);
+int loss_dispatch_17_24(int D, bool ident, int vec, bool bwd, const LossArgs& a, int gx, cudaStream_t s);
+int loss_dispatch_25_32(int D, bool ident, int vec, bool bwd, const LossArgs& a, int gx, cudaStream_t s);
+
+}  // namespace dml

@@ -1,0 +1,628 @@
+// Exact, tie-aware AUROC / AUPR / FPR@recall on the GPU (north-star kernel (d)).
+//
+//   key-gen  : score -> order-preserving packed u32 key, positive flag in bit 0
+//   sort     : ood_sort.cu (segmented LSD radix sort)
+//   scan     : segmented scan over distinct-score groups -> per-tile partial sums
+//   finalize : fixed-order reduction of the partials -> (auroc, aupr, fpr) per segment
+//
+// Replaces anomaly/anom_utils.py:25-78 (fpr_and_fdr_at_recall, get_measures -> sklearn
+// roc_auc_score / average_precision_score) and the callers' masking at
+// anomaly/eval_ood_traditional.py:128-148.  Math, groups g of equal
+// score in descending-score order, cumulative tps_g / fps_g:
+//   AUROC = sum_g neg_g (2 tps_g - pos_g) / (2 P N)        [== trapezoid over the ROC points]
+//   AUPR  = sum_g pos_g * tps_g / (tps_g + fps_g) / P
+//   FPR   = fps_{g*} / N,  g* = argmin_g |tps_g / P - recall| over groups with tps_{g-1} < P,
+//           ties -> the LATER group (anom_utils.py:57-65 scans from the lowest threshold down).
+#include "ood_sort.cuh"
+
+namespace dml {
+
+namespace {
+
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 16;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+constexpr int SCAN_WARPS = SCAN_THREADS / 32;
+
+// ---------------------------------------------------------------------------------------------
+// key generation
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t pack_key(float v, int kind, bool pos, uint32_t key_base, unsigned& n_nan,
+                                             unsigned& n_oow) {
+  float f = kind == 0 ? v : -v;
+  if (f != f) {
+    ++n_nan;
+    return 0xfffffffeu | (pos ? 1u : 0u);
+  }
+  if (f == 0.f) f = 0.f;  // -0 and +0 are one threshold
+  const uint32_t u = __float_as_uint(f);
+  const uint32_t srt = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+  uint32_t rel = srt - key_base;
+  if (srt < key_base || rel >= 0x80000000u) {
+    ++n_oow;
+    rel = srt < key_base ? 0u : 0x7fffffffu;
+  }
+  return (rel << 1) | (pos ? 1u : 0u);
+}
+
+template <typename GT>
+__device__ __forceinline__ bool is_positive(const GT* gt, const uint8_t* pos_u8, uint64_t mask, size_t i) {
+  if (pos_u8) return pos_u8[i] != 0;
+  const long long g = (long long)gt[i];
+  return g >= 0 && g < 64 && ((mask >> g) & 1ull);
+}
+
+template <typename GT>
+__global__ void __launch_bounds__(256) keygen_kernel(const float* __restrict__ values, const float* __restrict__ minmax,
+                                                     int slot, float* conf_out, const GT* __restrict__ gt,
+                                                     uint64_t out_mask, const uint8_t* __restrict__ pos_u8, int kind,
+                                                     long long seg_len, uint32_t key_base, uint32_t* __restrict__ keys,
+                                                     unsigned long long* seg_stats) {
+  const int seg = blockIdx.y;
+  const size_t base = (size_t)seg * (size_t)seg_len;
+  float lo = 0.f, den = 1.f;
+  const bool norm = minmax != nullptr;
+  if (norm) {
+    lo = minmax[seg * 4 + slot * 2];
+    den = __fsub_rn(minmax[seg * 4 + slot * 2 + 1], lo);
+  }
+  unsigned n_pos = 0, n_nan = 0, n_oow = 0;
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < seg_len; p += (long long)gridDim.x * blockDim.x) {
+    const size_t i = base + (size_t)p;
+    float v = values[i];
+    if (norm) v = __fdiv_rn(__fsub_rn(v, lo), den);  // NumPy: (x - min) / (max - min), fp32
+    if (conf_out) conf_out[i] = v;
+    const bool pos = is_positive(gt, pos_u8, out_mask, i);
+    n_pos += pos;
+    keys[i] = pack_key(v, kind, pos, key_base, n_nan, n_oow);
+  }
+  // block reduce the three counters
+  __shared__ unsigned s_c[3][8];
+  unsigned c[3] = {n_pos, n_nan, n_oow};
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c[j] += __shfl_xor_sync(0xffffffffu, c[j], o);
+    if ((threadIdx.x & 31) == 0) s_c[j][threadIdx.x >> 5] = c[j];
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    unsigned t = 0;
+    for (int wv = 0; wv < 8; ++wv) t += s_c[threadIdx.x][wv];
+    if (t) atomicAdd(seg_stats + (size_t)seg * 4 + threadIdx.x, (unsigned long long)t);
+  }
+}
+
+// min / max of the sortable key + NaN / positive counts (for choosing key_base on arbitrary scores)
+__global__ void __launch_bounds__(256) keystats_kernel(const float* __restrict__ values, int kind, long long seg_len,
+                                                       unsigned long long* seg_stats /*[seg,4]: min, max, n_nan, -*/) {
+  const int seg = blockIdx.y;
+  const size_t base = (size_t)seg * (size_t)seg_len;
+  uint32_t mn = 0xffffffffu, mx = 0u;
+  unsigned n_nan = 0;
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < seg_len; p += (long long)gridDim.x * blockDim.x) {
+    float f = values[base + (size_t)p];
+    f = kind == 0 ? f : -f;
+    if (f != f) { ++n_nan; continue; }
+    if (f == 0.f) f = 0.f;
+    const uint32_t u = __float_as_uint(f);
+    const uint32_t srt = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+    mn = min(mn, srt);
+    mx = max(mx, srt);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    n_nan += __shfl_xor_sync(0xffffffffu, n_nan, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicMin(seg_stats + (size_t)seg * 4 + 0, (unsigned long long)mn);
+    atomicMax(seg_stats + (size_t)seg * 4 + 1, (unsigned long long)mx);
+    if (n_nan) atomicAdd(seg_stats + (size_t)seg * 4 + 2, (unsigned long long)n_nan);
+  }
+}
+
+__global__ void keystats_init_kernel(unsigned long long* s, int n_seg) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_seg) { s[i * 4 + 0] = 0xffffffffull; s[i * 4 + 1] = 0ull; s[i * 4 + 2] = 0ull; s[i * 4 + 3] = 0ull; }
+}
+
+// ---------------------------------------------------------------------------------------------
+// segmented scan over score groups
+// ---------------------------------------------------------------------------------------------
+struct Agg {  // tile-local counts (<= SCAN_TILE)
+  unsigned pos, spos, slen, head;
+};
+__device__ __forceinline__ Agg agg_combine(const Agg& a, const Agg& b) {
+  Agg r;
+  r.pos = a.pos + b.pos;
+  r.spos = b.head ? b.spos : a.spos + b.spos;
+  r.slen = b.head ? b.slen : a.slen + b.slen;
+  r.head = a.head | b.head;
+  return r;
+}
+__device__ __forceinline__ Agg agg_shfl_up(const Agg& a, int o) {
+  Agg r;
+  r.pos = __shfl_up_sync(0xffffffffu, a.pos, o);
+  r.spos = __shfl_up_sync(0xffffffffu, a.spos, o);
+  r.slen = __shfl_up_sync(0xffffffffu, a.slen, o);
+  r.head = __shfl_up_sync(0xffffffffu, a.head, o);
+  return r;
+}
+
+struct Carry {  // running state across tiles (64-bit)
+  unsigned long long pos, spos, slen;
+};
+struct TilePartial {
+  unsigned long long auroc_num;
+  double ap_sum;
+  double best_dist;
+  long long best_idx;
+  long long best_fps;
+  long long n_groups;
+};
+
+struct RangeInfo {  // device-resident description of one scan range (segment)
+  long long pos_before;  // positives ranked before this range
+  long long idx_before;  // elements ranked before this range
+  long long total_pos;   // P over the whole ranking
+  long long total_n;     // P + N over the whole ranking
+};
+
+// Loads one tile into registers in BLOCKED order (thread t: elements t*16 .. t*16+15) through a
+// padded shared buffer (coalesced global reads, conflict-free strided smem reads), plus the element
+// just before / after each thread's run for group-boundary detection.
+struct TileKeys {
+  uint32_t k[SCAN_ITEMS];
+  uint32_t prev, next;  // element before k[0] / after k[15]
+  bool has_prev, has_next;
+};
+
+__device__ __forceinline__ int pad_idx(int i) { return i + (i >> 4); }
+
+__device__ __forceinline__ void load_tile(const uint32_t* __restrict__ keys, long long n, long long tile_off,
+                                          uint32_t* s_keys /*[SCAN_TILE + SCAN_TILE/16 + 2]*/, TileKeys& tk) {
+  const int tid = threadIdx.x;
+#pragma unroll
+  for (int j = 0; j < SCAN_ITEMS; ++j) {
+    const int i = j * SCAN_THREADS + tid;
+    const long long g = tile_off + i;
+    s_keys[pad_idx(i)] = g < n ? keys[g] : 0u;
+  }
+  __shared__ uint32_t s_edge[2];
+  if (tid == 0) {
+    s_edge[0] = tile_off > 0 ? keys[tile_off - 1] : 0u;
+    s_edge[1] = tile_off + SCAN_TILE < n ? keys[tile_off + SCAN_TILE] : 0u;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < SCAN_ITEMS; ++j) tk.k[j] = s_keys[pad_idx(tid * SCAN_ITEMS + j)];
+  const long long first = tile_off + (long long)tid * SCAN_ITEMS;
+  tk.has_prev = first > 0;
+  tk.prev = tid > 0 ? s_keys[pad_idx(tid * SCAN_ITEMS - 1)] : s_edge[0];
+  tk.has_next = first + SCAN_ITEMS < n;
+  tk.next = tid < SCAN_THREADS - 1 ? s_keys[pad_idx((tid + 1) * SCAN_ITEMS)] : s_edge[1];
+}
+
+__device__ __forceinline__ Agg thread_aggregate(const TileKeys& tk, long long n, long long first) {
+  Agg a = {0u, 0u, 0u, 0u};
+  uint32_t prev = tk.prev;
+  bool have_prev = tk.has_prev;
+#pragma unroll
+  for (int j = 0; j < SCAN_ITEMS; ++j) {
+    if (first + j < n) {
+      const uint32_t k = tk.k[j];
+      const bool head = !have_prev || ((k >> 1) != (prev >> 1));
+      const unsigned p = k & 1u;
+      if (head) { a.spos = 0; a.slen = 0; a.head = 1; }
+      a.pos += p; a.spos += p; a.slen += 1;
+      prev = k; have_prev = true;
+    }
+  }
+  return a;
+}
+
+// phase 1: per-tile aggregate
+__global__ void __launch_bounds__(SCAN_THREADS) scan_agg_kernel(const uint32_t* __restrict__ keys, long long seg_len,
+                                                                int tiles_per_seg, Agg* __restrict__ tile_agg) {
+  __shared__ uint32_t s_keys[SCAN_TILE + SCAN_TILE / 16 + 2];
+  __shared__ Agg s_w[SCAN_WARPS];
+  const int seg = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const uint32_t* k = keys + (size_t)seg * (size_t)seg_len;
+  const long long tile_off = (long long)tile * SCAN_TILE;
+  TileKeys tk;
+  load_tile(k, seg_len, tile_off, s_keys, tk);
+  Agg a = thread_aggregate(tk, seg_len, tile_off + (long long)tid * SCAN_ITEMS);
+  // ordered inclusive warp scan, keep the last lane's value
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    Agg nb = agg_shfl_up(a, o);
+    if (lane >= o) a = agg_combine(nb, a);
+  }
+  if (lane == 31) s_w[w] = a;
+  __syncthreads();
+  if (tid == 0) {
+    Agg t = s_w[0];
+    for (int i = 1; i < SCAN_WARPS; ++i) t = agg_combine(t, s_w[i]);
+    tile_agg[(size_t)seg * tiles_per_seg + tile] = t;
+  }
+}
+
+// phase 2: exclusive scan of the tile aggregates of each segment -> carry-in per tile
+constexpr int CARRY_THREADS = 1024;
+__device__ __forceinline__ void carry_apply(Carry& c, unsigned& chead, const Agg& b) {
+  c.pos += b.pos;
+  if (b.head) { c.spos = b.spos; c.slen = b.slen; chead = 1; }
+  else { c.spos += b.spos; c.slen += b.slen; }
+}
+struct CarryH { Carry c; unsigned head; };
+__device__ __forceinline__ CarryH carryh_combine(const CarryH& a, const CarryH& b) {
+  CarryH r;
+  r.c.pos = a.c.pos + b.c.pos;
+  r.c.spos = b.head ? b.c.spos : a.c.spos + b.c.spos;
+  r.c.slen = b.head ? b.c.slen : a.c.slen + b.c.slen;
+  r.head = a.head | b.head;
+  return r;
+}
+__global__ void __launch_bounds__(CARRY_THREADS) scan_carry_kernel(const Agg* __restrict__ tile_agg, int tiles_per_seg,
+                                                                   const RangeInfo* __restrict__ info,
+                                                                   Carry* __restrict__ tile_carry) {
+  __shared__ CarryH s_t[CARRY_THREADS];
+  const int seg = blockIdx.x, tid = threadIdx.x;
+  const Agg* ag = tile_agg + (size_t)seg * tiles_per_seg;
+  Carry* out = tile_carry + (size_t)seg * tiles_per_seg;
+  const int per = (tiles_per_seg + CARRY_THREADS - 1) / CARRY_THREADS;
+  const int b = tid * per;
+  int e = b + per;
+  if (e > tiles_per_seg) e = tiles_per_seg;
+  CarryH mine;
+  mine.c.pos = mine.c.spos = mine.c.slen = 0ull;
+  mine.head = 0;
+  for (int i = b; i < e; ++i) carry_apply(mine.c, mine.head, ag[i]);
+  s_t[tid] = mine;
+  __syncthreads();
+  // Hillis-Steele inclusive scan over the per-thread aggregates (ordered operator)
+  for (int o = 1; o < CARRY_THREADS; o <<= 1) {
+    CarryH v = s_t[tid];
+    if (tid >= o) v = carryh_combine(s_t[tid - o], v);
+    __syncthreads();
+    s_t[tid] = v;
+    __syncthreads();
+  }
+  CarryH run;
+  run.c.pos = (unsigned long long)info[seg].pos_before;  // the range starts on a group boundary
+  run.c.spos = run.c.slen = 0ull;
+  run.head = 0;
+  if (tid > 0) run = carryh_combine(run, s_t[tid - 1]);
+  for (int i = b; i < e; ++i) {
+    out[i] = run.c;
+    carry_apply(run.c, run.head, ag[i]);
+  }
+}
+
+__device__ __forceinline__ bool best_better(double da, long long ia, double db, long long ib) {
+  return da < db || (da == db && ia > ib);
+}
+
+// phase 3: per-tile group contributions
+__global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(const uint32_t* __restrict__ keys, long long seg_len,
+                                                                  int tiles_per_seg, const Carry* __restrict__ tile_carry,
+                                                                  const RangeInfo* __restrict__ info, double recall_level,
+                                                                  TilePartial* __restrict__ partials) {
+  __shared__ uint32_t s_keys[SCAN_TILE + SCAN_TILE / 16 + 2];
+  __shared__ Agg s_w[SCAN_WARPS];
+  __shared__ TilePartial s_p[SCAN_WARPS];
+  const int seg = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const uint32_t* k = keys + (size_t)seg * (size_t)seg_len;
+  const long long tile_off = (long long)tile * SCAN_TILE;
+  const long long first = tile_off + (long long)tid * SCAN_ITEMS;
+  TileKeys tk;
+  load_tile(k, seg_len, tile_off, s_keys, tk);
+  const Agg mine = thread_aggregate(tk, seg_len, first);
+  // exclusive block scan of the thread aggregates
+  Agg incl = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    Agg nb = agg_shfl_up(incl, o);
+    if (lane >= o) incl = agg_combine(nb, incl);
+  }
+  if (lane == 31) s_w[w] = incl;
+  __syncthreads();
+  Agg excl = agg_shfl_up(incl, 1);
+  if (lane == 0) excl = Agg{0u, 0u, 0u, 0u};
+  Agg wpre = {0u, 0u, 0u, 0u};
+  for (int i = 0; i < w; ++i) wpre = agg_combine(wpre, s_w[i]);
+  excl = agg_combine(wpre, excl);
+
+  const Carry tc = tile_carry[(size_t)seg * tiles_per_seg + tile];
+  unsigned long long P = tc.pos + excl.pos;
+  unsigned long long spos = excl.head ? excl.spos : tc.spos + excl.spos;
+  unsigned long long slen = excl.head ? excl.slen : tc.slen + excl.slen;
+
+  const RangeInfo ri = info[seg];
+  const unsigned long long Ptot = (unsigned long long)ri.total_pos;
+  const double dP = (double)ri.total_pos;
+
+  unsigned long long auroc = 0ull;
+  double ap = 0.0;
+  double bdist = __longlong_as_double(0x7ff0000000000000ll);  // +inf
+  long long bidx = -1, bfps = 0, ngroups = 0;
+
+  uint32_t prev = tk.prev;
+  bool have_prev = tk.has_prev;
+#pragma unroll
+  for (int j = 0; j < SCAN_ITEMS; ++j) {
+    const long long gi = first + j;
+    if (gi < seg_len) {
+      const uint32_t key = tk.k[j];
+      const bool head = !have_prev || ((key >> 1) != (prev >> 1));
+      const unsigned p = key & 1u;
+      if (head) { spos = 0; slen = 0; }
+      P += p; spos += p; slen += 1;
+      prev = key; have_prev = true;
+      // group end: the next element (if any) opens a new group
+      bool endg;
+      if (gi + 1 >= seg_len) endg = true;
+      else {
+        const uint32_t nk = (j + 1 < SCAN_ITEMS) ? tk.k[(j + 1) % SCAN_ITEMS] : tk.next;
+        endg = (nk >> 1) != (key >> 1);
+      }
+      if (endg) {
+        const unsigned long long n_so_far = (unsigned long long)(ri.idx_before + gi + 1);
+        const unsigned long long neg_g = slen - spos;
+        const unsigned long long fps = n_so_far - P;
+        auroc += neg_g * (2ull * P - spos);
+        if (spos) ap += (double)spos * ((double)P / (double)n_so_far);
+        if (P - spos < Ptot) {
+          const double dist = fabs((double)P / dP - recall_level);
+          const long long idx = ri.idx_before + gi;
+          if (best_better(dist, idx, bdist, bidx)) { bdist = dist; bidx = idx; bfps = (long long)fps; }
+        }
+        ++ngroups;
+      }
+    }
+  }
+  // block reduction (fixed order)
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    auroc += __shfl_down_sync(0xffffffffu, auroc, o);
+    ap += __shfl_down_sync(0xffffffffu, ap, o);
+    ngroups += __shfl_down_sync(0xffffffffu, ngroups, o);
+    const double od = __shfl_down_sync(0xffffffffu, bdist, o);
+    const long long oi = __shfl_down_sync(0xffffffffu, bidx, o);
+    const long long of = __shfl_down_sync(0xffffffffu, bfps, o);
+    if (best_better(od, oi, bdist, bidx)) { bdist = od; bidx = oi; bfps = of; }
+  }
+  if (lane == 0) {
+    TilePartial t;
+    t.auroc_num = auroc; t.ap_sum = ap; t.best_dist = bdist; t.best_idx = bidx; t.best_fps = bfps; t.n_groups = ngroups;
+    s_p[w] = t;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    TilePartial t = s_p[0];
+    for (int i = 1; i < SCAN_WARPS; ++i) {
+      t.auroc_num += s_p[i].auroc_num;
+      t.ap_sum += s_p[i].ap_sum;
+      t.n_groups += s_p[i].n_groups;
+      if (best_better(s_p[i].best_dist, s_p[i].best_idx, t.best_dist, t.best_idx)) {
+        t.best_dist = s_p[i].best_dist; t.best_idx = s_p[i].best_idx; t.best_fps = s_p[i].best_fps;
+      }
+    }
+    partials[(size_t)seg * tiles_per_seg + tile] = t;
+  }
+}
+
+// phase 4: fixed-order reduction of the tile partials of each segment
+constexpr int FIN_THREADS = 256;
+__device__ __forceinline__ void partial_merge(TilePartial& a, const TilePartial& b) {
+  a.auroc_num += b.auroc_num;
+  a.ap_sum += b.ap_sum;
+  a.n_groups += b.n_groups;
+  if (best_better(b.best_dist, b.best_idx, a.best_dist, a.best_idx)) {
+    a.best_dist = b.best_dist; a.best_idx = b.best_idx; a.best_fps = b.best_fps;
+  }
+}
+__global__ void __launch_bounds__(FIN_THREADS) scan_finalize_kernel(const TilePartial* __restrict__ partials, int tiles_per_seg,
+                                                                    const RangeInfo* __restrict__ info,
+                                                                    const unsigned long long* __restrict__ seg_stats,
+                                                                    dml_ood_result* __restrict__ results,
+                                                                    TilePartial* __restrict__ range_partials) {
+  __shared__ TilePartial s_t[FIN_THREADS];
+  const int seg = blockIdx.x, tid = threadIdx.x;
+  const TilePartial* pp = partials + (size_t)seg * tiles_per_seg;
+  TilePartial t;
+  t.auroc_num = 0ull; t.ap_sum = 0.0; t.best_dist = __longlong_as_double(0x7ff0000000000000ll);
+  t.best_idx = -1; t.best_fps = 0; t.n_groups = 0;
+  // contiguous chunk per thread => the same summation order regardless of scheduling
+  const int per = (tiles_per_seg + FIN_THREADS - 1) / FIN_THREADS;
+  const int b = tid * per;
+  int e = b + per;
+  if (e > tiles_per_seg) e = tiles_per_seg;
+  for (int i = b; i < e; ++i) partial_merge(t, pp[i]);
+  s_t[tid] = t;
+  __syncthreads();
+  for (int o = FIN_THREADS / 2; o > 0; o >>= 1) {
+    if (tid < o) {
+      TilePartial a = s_t[tid];
+      partial_merge(a, s_t[tid + o]);
+      s_t[tid] = a;
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    const TilePartial r = s_t[0];
+    if (range_partials) range_partials[seg] = r;
+    if (results) {
+      const RangeInfo ri = info[seg];
+      const double P = (double)ri.total_pos, N = (double)(ri.total_n - ri.total_pos);
+      dml_ood_result o;
+      o.n_pos = ri.total_pos;
+      o.n_neg = ri.total_n - ri.total_pos;
+      o.n_nan = seg_stats ? (long long)seg_stats[(size_t)seg * 4 + 1] : 0;
+      o.n_groups = r.n_groups;
+      if (ri.total_pos > 0 && o.n_neg > 0) {
+        o.auroc = (double)r.auroc_num / (2.0 * P * N);
+        o.aupr = r.ap_sum / P;
+        o.fpr = (double)r.best_fps / N;
+      } else {
+        const double nan = __longlong_as_double(0x7ff8000000000000ll);
+        o.auroc = o.aupr = o.fpr = nan;
+      }
+      results[seg] = o;
+    }
+  }
+}
+
+// RangeInfo of whole segments: everything starts at zero, totals from the key-gen statistics
+__global__ void range_info_from_stats_kernel(const unsigned long long* __restrict__ seg_stats, long long seg_len, int n_seg,
+                                             RangeInfo* __restrict__ info) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_seg) {
+    RangeInfo r;
+    r.pos_before = 0; r.idx_before = 0;
+    r.total_pos = (long long)seg_stats[(size_t)i * 4 + 0];
+    r.total_n = seg_len;
+    info[i] = r;
+  }
+}
+
+struct MetricsPlan {
+  SortPlan sort;
+  int tiles_per_seg;  // scan tiles
+  size_t off_agg, off_carry, off_partial, off_info, off_end;
+};
+
+MetricsPlan make_metrics_plan(int n_seg, long long seg_len) {
+  MetricsPlan m;
+  m.sort = make_sort_plan(n_seg, seg_len, 0, 32);
+  m.tiles_per_seg = (int)((seg_len + SCAN_TILE - 1) / SCAN_TILE);
+  if (m.tiles_per_seg < 1) m.tiles_per_seg = 1;
+  auto align = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  const size_t nt = (size_t)n_seg * m.tiles_per_seg;
+  m.off_agg = m.sort.off_end;
+  m.off_carry = align(m.off_agg + nt * sizeof(Agg));
+  m.off_partial = align(m.off_carry + nt * sizeof(Carry));
+  m.off_info = align(m.off_partial + nt * sizeof(TilePartial));
+  m.off_end = align(m.off_info + (size_t)n_seg * sizeof(RangeInfo));
+  return m;
+}
+
+int run_scan(const uint32_t* sorted, const MetricsPlan& m, unsigned char* ws, const RangeInfo* info, double recall_level,
+             const unsigned long long* seg_stats, dml_ood_result* results, TilePartial* range_partials, cudaStream_t stream) {
+  Agg* agg = reinterpret_cast<Agg*>(ws + m.off_agg);
+  Carry* carry = reinterpret_cast<Carry*>(ws + m.off_carry);
+  TilePartial* partial = reinterpret_cast<TilePartial*>(ws + m.off_partial);
+  dim3 grid((unsigned)m.tiles_per_seg, (unsigned)m.sort.n_seg);
+  scan_agg_kernel<<<grid, SCAN_THREADS, 0, stream>>>(sorted, m.sort.seg_len, m.tiles_per_seg, agg);
+  DML_LAUNCH_CHECK();
+  scan_carry_kernel<<<m.sort.n_seg, CARRY_THREADS, 0, stream>>>(agg, m.tiles_per_seg, info, carry);
+  DML_LAUNCH_CHECK();
+  scan_apply_kernel<<<grid, SCAN_THREADS, 0, stream>>>(sorted, m.sort.seg_len, m.tiles_per_seg, carry, info, recall_level, partial);
+  DML_LAUNCH_CHECK();
+  scan_finalize_kernel<<<m.sort.n_seg, FIN_THREADS, 0, stream>>>(partial, m.tiles_per_seg, info, seg_stats, results, range_partials);
+  DML_LAUNCH_CHECK();
+  return DML_OK;
+}
+
+}  // namespace
+}  // namespace dml
+
+using namespace dml;
+
+extern "C" {
+#pragma GCC visibility push(default)
+
+int dml_ood_keystats(const float* values, int32_t score_kind, int32_t n_seg, int64_t seg_len, long long* seg_stats,
+                     dml_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!values || !seg_stats || n_seg < 0 || seg_len < 0 || n_seg > 65535) return DML_ERR_INVALID_ARG;
+  if (n_seg == 0) return DML_OK;
+  keystats_init_kernel<<<ceil_div_i(n_seg, 256), 256, 0, stream>>>((unsigned long long*)seg_stats, n_seg);
+  DML_LAUNCH_CHECK();
+  if (seg_len == 0) return DML_OK;
+  long long bx = (seg_len + 256 * 16 - 1) / (256 * 16);
+  const long long cap = n_seg >= 148 * 8 ? 8 : (148 * 16) / n_seg + 1;
+  if (bx > cap) bx = cap;
+  keystats_kernel<<<dim3((unsigned)bx, (unsigned)n_seg), 256, 0, stream>>>(values, score_kind, seg_len,
+                                                                            (unsigned long long*)seg_stats);
+  DML_LAUNCH_CHECK();
+  return DML_OK;
+}
+
+int dml_ood_keygen(const float* values, const float* minmax, int32_t minmax_slot, float* conf_out, const uint8_t* gt_u8,
+                   const int64_t* gt_i64, uint64_t out_label_mask, const uint8_t* pos_u8, int32_t score_kind,
+                   uint32_t key_base, int32_t n_seg, int64_t seg_len, uint32_t* keys, long long* seg_stats,
+                   dml_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!values || !keys || !seg_stats || n_seg < 0 || seg_len < 0 || n_seg > 65535) return DML_ERR_INVALID_ARG;
+  const int nsrc = (gt_u8 != nullptr) + (gt_i64 != nullptr) + (pos_u8 != nullptr);
+  if (nsrc != 1) return DML_ERR_INVALID_ARG;
+  if (minmax && (minmax_slot < 0 || minmax_slot > 1)) return DML_ERR_INVALID_ARG;
+  if (score_kind != 0 && score_kind != 1) return DML_ERR_INVALID_ARG;
+  if (n_seg == 0) return DML_OK;
+  DML_CUDA_TRY(cudaMemsetAsync(seg_stats, 0, (size_t)n_seg * 4 * sizeof(long long), stream));
+  if (seg_len == 0) return DML_OK;
+  long long bx = (seg_len + 256 * 8 - 1) / (256 * 8);
+  const long long cap = n_seg >= 148 * 8 ? 16 : (148 * 32) / n_seg + 1;
+  if (bx > cap) bx = cap;
+  dim3 grid((unsigned)bx, (unsigned)n_seg);
+  unsigned long long* st = (unsigned long long*)seg_stats;
+  if (gt_i64)
+    keygen_kernel<long long><<<grid, 256, 0, stream>>>(values, minmax, minmax_slot, conf_out, (const long long*)gt_i64,
+                                                       out_label_mask, nullptr, score_kind, seg_len, key_base, keys, st);
+  else
+    keygen_kernel<uint8_t><<<grid, 256, 0, stream>>>(values, minmax, minmax_slot, conf_out, gt_u8, out_label_mask, pos_u8,
+                                                     score_kind, seg_len, key_base, keys, st);
+  DML_LAUNCH_CHECK();
+  return DML_OK;
+}
+
+size_t dml_ood_workspace_bytes(int32_t n_seg, int64_t seg_len) {
+  if (n_seg <= 0 || seg_len <= 0) return 256;
+  return make_metrics_plan(n_seg, seg_len).off_end;
+}
+
+int dml_ood_eval_segments(uint32_t* keys, const long long* seg_stats, int32_t n_seg, int64_t seg_len, double recall_level,
+                          void* workspace, size_t workspace_bytes, dml_ood_result* results, dml_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!keys || !seg_stats || !workspace || !results || n_seg < 0 || seg_len < 0 || n_seg > 65535) return DML_ERR_INVALID_ARG;
+  if (seg_len >= (1ll << 32)) return DML_ERR_INVALID_ARG;
+  if (n_seg == 0) return DML_OK;
+  const MetricsPlan m = make_metrics_plan(n_seg, seg_len);
+  if (workspace_bytes < m.off_end) return DML_ERR_WORKSPACE;
+  unsigned char* ws = reinterpret_cast<unsigned char*>(workspace);
+  uint32_t* sorted = keys;
+  if (seg_len > 0) {
+    int rc = radix_sort_segments(keys, m.sort, workspace, &sorted, stream);
+    if (rc != DML_OK) return rc;
+  }
+  RangeInfo* info = reinterpret_cast<RangeInfo*>(ws + m.off_info);
+  range_info_from_stats_kernel<<<ceil_div_i(n_seg, 256), 256, 0, stream>>>((const unsigned long long*)seg_stats, seg_len, n_seg, info);
+  DML_LAUNCH_CHECK();
+  return run_scan(sorted, m, ws, info, recall_level, (const unsigned long long*)seg_stats, results, nullptr, stream);
+}
+
+int dml_ood_sort(uint32_t* keys, int32_t n_seg, int64_t seg_len, int32_t begin_bit, int32_t end_bit, void* workspace,
+                 size_t workspace_bytes, uint32_t** sorted_out, dml_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!keys || !workspace || !sorted_out || n_seg < 0 || seg_len < 0 || n_seg > 65535) return DML_ERR_INVALID_ARG;
+  if (begin_bit < 0 || end_bit > 32 || begin_bit > end_bit || seg_len >= (1ll << 32)) return DML_ERR_INVALID_ARG;
+  const SortPlan plan = make_sort_plan(n_seg, seg_len, begin_bit, end_bit);
+  if (workspace_bytes < plan.off_end) return DML_ERR_WORKSPACE;
+  return radix_sort_segments(keys, plan, workspace, sorted_out, stream);
+}
+
+int dml_ood_scan_range(const uint32_t* sorted_keys, int64_t n, const long long* range_info, double recall_level,
+                       void* workspace, size_t workspace_bytes, void* partial_out, dml_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!sorted_keys || !range_info || !workspace || !partial_out || n < 0 || n >= (1ll << 32)) return DML_ERR_INVALID_ARG;
+  const MetricsPlan m = make_metrics_plan(1, n);
+  if (workspace_bytes < m.off_end) return DML_ERR_WORKSPACE;
+  return run_scan(sorted_keys, m, reinterpret_cast<unsigned char*>(workspace), reinterpret_cast<const RangeInfo*>(range_info),
+                  recall_level, nullptr, nullptr, reinterpret_cast<TilePartial*>(partial_out), stream);
+}
+
+#pragma GCC visibility pop
+}  // extern "C"

@@ -1,0 +1,279 @@
+// Segmented one-read/one-write-per-pass LSD radix sort (see ood_sort.cuh).
+#include "ood_sort.cuh"
+
+namespace dml {
+
+namespace {
+
+__device__ __forceinline__ unsigned lanemask_lt() {
+  unsigned m;
+  asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+  return m;
+}
+
+// ---- digit histograms of every pass in one read of the keys --------------------------------
+// Warp-private shared histograms updated by the match-group leader with plain LDS/STS (no atomics).
+constexpr int HIST_TILES_PER_BLOCK = 16;
+
+__global__ void __launch_bounds__(SORT_THREADS) hist_kernel(const uint32_t* __restrict__ keys, long long seg_len,
+                                                            int n_passes, int s0, int s1, int s2, int s3,
+                                                            uint32_t* __restrict__ ghist) {
+  __shared__ uint32_t s_h[SORT_WARPS][MAX_PASSES][RADIX];  // 32 KB
+  const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < SORT_WARPS * MAX_PASSES * RADIX; i += SORT_THREADS) (&s_h[0][0][0])[i] = 0u;
+  __syncthreads();
+  const int seg = blockIdx.y;
+  const uint32_t* k = keys + (size_t)seg * seg_len;
+  const long long chunk = (long long)HIST_TILES_PER_BLOCK * SORT_TILE;
+  const long long begin = (long long)blockIdx.x * chunk;
+  long long end = begin + chunk;
+  if (end > seg_len) end = seg_len;
+  const int shifts[MAX_PASSES] = {s0, s1, s2, s3};
+  // each warp walks its own contiguous slice, 32 keys per step (uniform trip count per warp)
+  const long long per_warp = chunk / SORT_WARPS;
+  const long long wbeg = begin + (long long)w * per_warp;
+  constexpr int U = 8;  // independent 128-byte warp loads in flight per step
+  for (long long off = 0; off < per_warp; off += 32 * U) {
+    if (wbeg + off >= end) break;  // warp-uniform
+    uint32_t key[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long i = wbeg + off + u * 32 + lane;
+      key[u] = i < end ? __ldg(k + i) : 0u;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const bool valid = (wbeg + off + u * 32 + lane) < end;
+#pragma unroll
+      for (int p = 0; p < MAX_PASSES; ++p) {
+        if (p < n_passes) {
+          const uint32_t d = valid ? ((key[u] >> shifts[p]) & (RADIX - 1)) : 0xffffffffu;
+          const unsigned peers = __match_any_sync(0xffffffffu, d);
+          if (valid && lane == (__ffs(peers) - 1)) s_h[w][p][d] += (uint32_t)__popc(peers);
+          __syncwarp();
+        }
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < n_passes * RADIX; i += SORT_THREADS) {
+    const int p = i >> RADIX_BITS, d = i & (RADIX - 1);
+    uint32_t c = 0;
+#pragma unroll
+    for (int ww = 0; ww < SORT_WARPS; ++ww) c += s_h[ww][p][d];
+    if (c) atomicAdd(ghist + ((size_t)seg * MAX_PASSES + p) * RADIX + d, c);
+  }
+}
+
+// exclusive scan of each 256-bin histogram (one block per (segment, pass))
+__global__ void __launch_bounds__(RADIX) hist_scan_kernel(uint32_t* ghist) {
+  __shared__ uint32_t s_w[RADIX / 32];
+  uint32_t* h = ghist + (size_t)blockIdx.x * RADIX;
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+  const uint32_t c = h[t];
+  uint32_t incl = c;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t n = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += n;
+  }
+  if (lane == 31) s_w[w] = incl;
+  __syncthreads();
+  uint32_t base = 0;
+  for (int i = 0; i < w; ++i) base += s_w[i];
+  h[t] = base + incl - c;
+}
+
+template <typename LB>
+struct LbTraits;
+template <>
+struct LbTraits<uint32_t> {
+  static constexpr uint32_t LOCAL = 1u << 30, INCL = 2u << 30, MASK = (1u << 30) - 1;
+  static constexpr int FLAG_SHIFT = 30;
+};
+template <>
+struct LbTraits<unsigned long long> {
+  static constexpr unsigned long long LOCAL = LB_FLAG_LOCAL, INCL = LB_FLAG_INCL, MASK = LB_VALUE_MASK;
+  static constexpr int FLAG_SHIFT = 62;
+};
+
+template <typename LB>
+__global__ void __launch_bounds__(SORT_THREADS) onesweep_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out,
+                                                                long long seg_len, int tiles_per_seg, int shift, int pass,
+                                                                const uint32_t* __restrict__ ghist_excl, LB* lookback,
+                                                                uint32_t* tickets) {
+  using T = LbTraits<LB>;
+  __shared__ uint32_t s_whist[SORT_WARPS][RADIX];
+  __shared__ uint32_t s_keys[SORT_TILE];
+  __shared__ unsigned long long s_gbase[RADIX];
+  __shared__ uint32_t s_scan[SORT_WARPS];
+  __shared__ int s_tile;
+
+  const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+  const int seg = blockIdx.y;
+  if (tid == 0) s_tile = (int)atomicAdd(tickets + seg, 1u);
+  for (int i = tid; i < SORT_WARPS * RADIX; i += SORT_THREADS) (&s_whist[0][0])[i] = 0u;
+  __syncthreads();
+  const int tile = s_tile;
+  const size_t seg_base = (size_t)seg * (size_t)seg_len;
+  const long long tile_off = (long long)tile * SORT_TILE;
+  const long long rem = seg_len - tile_off;
+  const int nvalid = rem >= SORT_TILE ? SORT_TILE : (int)rem;
+
+  // ---- load (warp-striped inside the warp's contiguous slice => LSD-stable order) ----------
+  uint32_t key[SORT_ITEMS];
+  uint32_t rank[SORT_ITEMS];
+  const int wbase = w * 32 * SORT_ITEMS;
+  const uint32_t* src = in + seg_base + tile_off;
+#pragma unroll
+  for (int i = 0; i < SORT_ITEMS; ++i) {
+    const int idx = wbase + i * 32 + lane;
+    key[i] = idx < nvalid ? src[idx] : 0xffffffffu;
+  }
+  // ---- rank within warp ----------------------------------------------------------------------
+  const unsigned lt = lanemask_lt();
+#pragma unroll
+  for (int i = 0; i < SORT_ITEMS; ++i) {
+    const int idx = wbase + i * 32 + lane;
+    const bool valid = idx < nvalid;
+    const uint32_t d = valid ? ((key[i] >> shift) & (RADIX - 1)) : 0xffffffffu;
+    const unsigned peers = __match_any_sync(0xffffffffu, d);
+    const int leader = __ffs(peers) - 1;
+    uint32_t c = 0;
+    if (valid && lane == leader) {
+      c = s_whist[w][d];
+      s_whist[w][d] = c + (uint32_t)__popc(peers);
+    }
+    __syncwarp();
+    c = __shfl_sync(0xffffffffu, c, leader);
+    rank[i] = c + (uint32_t)__popc(peers & lt);
+  }
+  __syncthreads();
+
+  // ---- thread t owns digit t: prefix over warps, publish, look back ----------------------------
+  uint32_t run = 0;
+#pragma unroll
+  for (int ww = 0; ww < SORT_WARPS; ++ww) {
+    const uint32_t c = s_whist[ww][tid];
+    s_whist[ww][tid] = run;
+    run += c;
+  }
+  volatile LB* lb = lookback + ((size_t)seg * tiles_per_seg + tile) * RADIX;
+  lb[tid] = (LB)run | (tile == 0 ? T::INCL : T::LOCAL);
+
+  // exclusive scan of the tile's digit counts
+  uint32_t incl = run;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t n = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += n;
+  }
+  if (lane == 31) s_scan[w] = incl;
+  __syncthreads();
+  uint32_t dbase = incl - run;
+#pragma unroll
+  for (int i = 0; i < SORT_WARPS; ++i)
+    if (i < w) dbase += s_scan[i];
+
+  unsigned long long excl = 0;
+  if (tile > 0) {
+    int p = tile - 1;
+    while (true) {
+      volatile LB* q = lookback + ((size_t)seg * tiles_per_seg + p) * RADIX;
+      LB v;
+      do { v = q[tid]; } while ((v >> T::FLAG_SHIFT) == 0);
+      excl += (unsigned long long)(v & T::MASK);
+      if ((v >> T::FLAG_SHIFT) == 2) break;
+      --p;
+    }
+    lb[tid] = (LB)(excl + run) | T::INCL;
+  }
+  s_gbase[tid] = (unsigned long long)ghist_excl[((size_t)seg * MAX_PASSES + pass) * RADIX + tid] + excl - dbase;
+#pragma unroll
+  for (int ww = 0; ww < SORT_WARPS; ++ww) s_whist[ww][tid] += dbase;
+  __syncthreads();
+
+  // ---- local scatter into digit order, then coalesced runs to global -----------------------------
+#pragma unroll
+  for (int i = 0; i < SORT_ITEMS; ++i) {
+    const int idx = wbase + i * 32 + lane;
+    if (idx < nvalid) {
+      const uint32_t d = (key[i] >> shift) & (RADIX - 1);
+      s_keys[s_whist[w][d] + rank[i]] = key[i];
+    }
+  }
+  __syncthreads();
+  uint32_t* dst = out + seg_base;
+#pragma unroll
+  for (int j = 0; j < SORT_ITEMS; ++j) {
+    const int pos = j * SORT_THREADS + tid;
+    if (pos < nvalid) {
+      const uint32_t k = s_keys[pos];
+      const uint32_t d = (k >> shift) & (RADIX - 1);
+      dst[s_gbase[d] + (unsigned long long)pos] = k;
+    }
+  }
+}
+
+}  // namespace
+
+SortPlan make_sort_plan(int n_seg, long long seg_len, int begin_bit, int end_bit) {
+  SortPlan p;
+  p.n_seg = n_seg;
+  p.seg_len = seg_len;
+  p.tiles_per_seg = (int)((seg_len + SORT_TILE - 1) / SORT_TILE);
+  if (p.tiles_per_seg < 1) p.tiles_per_seg = 1;
+  p.n_passes = 0;
+  for (int b = begin_bit; b < end_bit && p.n_passes < MAX_PASSES; b += RADIX_BITS) p.shifts[p.n_passes++] = b;
+  for (int i = p.n_passes; i < MAX_PASSES; ++i) p.shifts[i] = 0;
+  auto align = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  const size_t n = (size_t)n_seg * (size_t)seg_len;
+  const size_t lb_entry = seg_len < (1ll << 30) ? sizeof(uint32_t) : sizeof(unsigned long long);
+  p.off_alt = 0;
+  p.off_hist = align(p.off_alt + n * sizeof(uint32_t));
+  p.off_lookback = align(p.off_hist + (size_t)n_seg * MAX_PASSES * RADIX * sizeof(uint32_t));
+  p.off_ticket = align(p.off_lookback + (size_t)n_seg * p.tiles_per_seg * RADIX * lb_entry);
+  p.off_end = align(p.off_ticket + (size_t)n_seg * sizeof(uint32_t));
+  return p;
+}
+
+int radix_sort_segments(uint32_t* keys, const SortPlan& plan, void* workspace, uint32_t** sorted, cudaStream_t stream) {
+  unsigned char* ws = reinterpret_cast<unsigned char*>(workspace);
+  uint32_t* alt = reinterpret_cast<uint32_t*>(ws + plan.off_alt);
+  uint32_t* ghist = reinterpret_cast<uint32_t*>(ws + plan.off_hist);
+  void* lookback = ws + plan.off_lookback;
+  uint32_t* tickets = reinterpret_cast<uint32_t*>(ws + plan.off_ticket);
+  const bool wide = plan.seg_len >= (1ll << 30);
+  if (plan.n_seg == 0 || plan.seg_len == 0 || plan.n_passes == 0) {
+    *sorted = keys;
+    return DML_OK;
+  }
+  DML_CUDA_TRY(cudaMemsetAsync(ghist, 0, plan.off_lookback - plan.off_hist, stream));
+  {
+    const long long chunk = (long long)HIST_TILES_PER_BLOCK * SORT_TILE;
+    dim3 grid((unsigned)((plan.seg_len + chunk - 1) / chunk), (unsigned)plan.n_seg);
+    hist_kernel<<<grid, SORT_THREADS, 0, stream>>>(keys, plan.seg_len, plan.n_passes, plan.shifts[0], plan.shifts[1],
+                                                   plan.shifts[2], plan.shifts[3], ghist);
+    DML_LAUNCH_CHECK();
+    hist_scan_kernel<<<plan.n_seg * MAX_PASSES, RADIX, 0, stream>>>(ghist);
+    DML_LAUNCH_CHECK();
+  }
+  uint32_t* in = keys;
+  uint32_t* out = alt;
+  dim3 grid((unsigned)plan.tiles_per_seg, (unsigned)plan.n_seg);
+  for (int p = 0; p < plan.n_passes; ++p) {
+    DML_CUDA_TRY(cudaMemsetAsync(lookback, 0, plan.off_end - plan.off_lookback, stream));  // look-back + tickets
+    if (wide)
+      onesweep_kernel<unsigned long long><<<grid, SORT_THREADS, 0, stream>>>(
+          in, out, plan.seg_len, plan.tiles_per_seg, plan.shifts[p], p, ghist, (unsigned long long*)lookback, tickets);
+    else
+      onesweep_kernel<uint32_t><<<grid, SORT_THREADS, 0, stream>>>(in, out, plan.seg_len, plan.tiles_per_seg,
+                                                                  plan.shifts[p], p, ghist, (uint32_t*)lookback, tickets);
+    DML_LAUNCH_CHECK();
+    uint32_t* t = in; in = out; out = t;
+  }
+  *sorted = in;
+  return DML_OK;
+}
+
+}  // namespace dml

@@ -1,0 +1,211 @@
+"""Exact, tie-aware AUROC / AUPR / FPR@recall on the GPU (kernel (d)) -- functional API.
+
+Replaces anomaly/anom_utils.py:25-78 (``fpr_and_fdr_at_recall``, ``get_measures`` with its two
+scikit-learn calls) and the per-image driver anomaly/eval_ood_traditional.py:128-148.
+Everything between the score map and the three numbers runs in libdml_b200.so: key
+generation, segmented radix sort, group scan, fixed-order reductions.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Iterable, Optional, Sequence
+
+import numpy as np
+import torch
+
+from ._lib import OOD_RESULT_WORDS, check, lib, ptr, require_cuda, stream_ptr
+
+RECALL_LEVEL_DEFAULT = 0.95       # anomaly/anom_utils.py:4
+KEY_BASE_NONNEG = 0x80000000      # sortable image of +0.0: any conf >= 0 fits the 31-bit window
+PARTIAL_WORDS = 6                 # u64 auroc_num, f64 ap_sum, f64 best_dist, i64 best_idx, i64 best_fps, i64 n_groups
+
+
+def label_mask(out_labels: Iterable[int]) -> int:
+    m = 0
+    for l in out_labels:
+        l = int(l)
+        if not 0 <= l < 64:
+            raise ValueError("out labels must lie in [0, 64)")
+        m |= 1 << l
+    return m
+
+
+class OodWorkspace:
+    """Grow-only device scratch (keys, sort/scan workspace, per-segment stats and results), so a
+    streaming evaluation does no allocation after warm-up."""
+
+    def __init__(self, device):
+        self.device = torch.device(device)
+        self._bufs = {}
+
+    def get(self, name: str, nbytes: int) -> torch.Tensor:
+        cur = self._bufs.get(name)
+        if cur is None or cur.numel() < nbytes:
+            cur = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=self.device)
+            self._bufs[name] = cur
+        return cur
+
+
+def _raise_on_bad_stats(stats: np.ndarray, what: str):
+    if (stats[:, 1] > 0).any():
+        raise ValueError("Input contains NaN.")           # sklearn's validation in the reference path
+    if (stats[:, 2] > 0).any():
+        raise ValueError(f"{what}: ranking keys outside the packed 31-bit window (wrong key_base)")
+
+
+def eval_segments(values: torch.Tensor, n_seg: int, seg_len: int, *, gt: Optional[torch.Tensor] = None,
+                  out_labels: Sequence[int] = (13,), positive: Optional[torch.Tensor] = None, score_kind: int = 0,
+                  key_base: int = KEY_BASE_NONNEG, minmax: Optional[torch.Tensor] = None, minmax_slot: int = 0,
+                  conf_out: Optional[torch.Tensor] = None, recall_level: float = RECALL_LEVEL_DEFAULT,
+                  workspace: Optional[OodWorkspace] = None):
+    """Evaluate ``n_seg`` independent segments of ``seg_len`` (score, label) pairs each.
+
+    values: flat fp32 CUDA tensor (n_seg*seg_len): a ``conf`` map ranked as score = -conf
+            (``score_kind=0``; positives expected at low conf) or plain scores (``score_kind=1``).
+    gt/out_labels: positives are pixels whose gt label is in ``out_labels``; or pass ``positive``
+            (uint8, non-zero = positive) directly.
+    minmax: optional [n_seg,4] per-segment (min,max) pairs; the kernel then ranks the min-max
+            normalised value (slot 0: eds, 1: msp) and can store it to ``conf_out``.
+    Returns (results, stats): device tensors -- results float64 [n_seg,7] viewed as
+    (auroc, aupr, fpr, n_pos, n_neg, n_nan, n_groups; the last four are int64 bit patterns),
+    stats int64 [n_seg,4] = (n_pos, n_nan, n_out_of_window, 0).  No host synchronisation.
+    """
+    require_cuda(values, "values")
+    dev = values.device
+    values = values.contiguous().view(-1)
+    if values.dtype != torch.float32 or values.numel() != n_seg * seg_len:
+        raise ValueError("values must be float32 with n_seg*seg_len elements")
+    ws = workspace or OodWorkspace(dev)
+    n = n_seg * seg_len
+    keys = ws.get("keys", 4 * n)
+    stats = ws.get("stats", 32 * max(n_seg, 1)).view(torch.int64)[: 4 * n_seg].view(n_seg, 4)
+    results = ws.get("results", 8 * OOD_RESULT_WORDS * max(n_seg, 1)).view(torch.float64)[: OOD_RESULT_WORDS * n_seg]
+    results = results.view(n_seg, OOD_RESULT_WORDS)
+    nbytes = lib().dml_ood_workspace_bytes(n_seg, seg_len)
+    scratch = ws.get("scratch", nbytes)
+    gt_u8 = gt_i64 = pos_u8 = None
+    if positive is not None:
+        pos_u8 = positive.contiguous().view(-1)
+        if pos_u8.dtype == torch.bool:
+            pos_u8 = pos_u8.view(torch.uint8)
+        if pos_u8.dtype != torch.uint8 or pos_u8.numel() != n:
+            raise ValueError("positive must be uint8/bool with one entry per value")
+    elif gt is not None:
+        g = gt.contiguous().view(-1)
+        if g.numel() != n:
+            raise ValueError("gt must have one entry per value")
+        if g.dtype == torch.uint8:
+            gt_u8 = g
+        elif g.dtype == torch.int64:
+            gt_i64 = g
+        else:
+            raise ValueError("gt must be uint8 or int64")
+    else:
+        raise ValueError("need gt or positive")
+    with torch.cuda.device(dev):
+        s = stream_ptr(dev)
+        check(lib().dml_ood_keygen(ptr(values), ptr(minmax), minmax_slot, ptr(conf_out), ptr(gt_u8), ptr(gt_i64),
+                                   label_mask(out_labels) if positive is None else 0, ptr(pos_u8), score_kind, key_base,
+                                   n_seg, seg_len, ptr(keys), ptr(stats), s), "dml_ood_keygen")
+        check(lib().dml_ood_eval_segments(ptr(keys), ptr(stats), n_seg, seg_len, recall_level, ptr(scratch),
+                                          scratch.numel(), ptr(results), s), "dml_ood_eval_segments")
+    return results, stats
+
+
+def results_to_host(results: torch.Tensor, stats: torch.Tensor, what: str = "ood metrics"):
+    """D2H copy + the reference's error behaviour: NaN scores -> ValueError (sklearn);
+    single-class segments come back as NaN rows (callers map them to ``None``)."""
+    r = results.cpu().numpy()
+    st = stats.cpu().numpy()
+    _raise_on_bad_stats(st, what)
+    return r[:, :3].copy(), r[:, 3:].view(np.int64).copy()
+
+
+# --------------------------------------------------------------------------------------------
+# arbitrary scores (any sign / range): choose the key window from the data
+# --------------------------------------------------------------------------------------------
+def _scan_sorted_range(sorted_keys_ptr: int, n: int, pos_before: int, idx_before: int, total_pos: int, total_n: int,
+                       recall_level: float, ws: OodWorkspace, dev) -> np.ndarray:
+    info = torch.tensor([pos_before, idx_before, total_pos, total_n], dtype=torch.int64, device=dev)
+    partial = torch.empty(PARTIAL_WORDS, dtype=torch.int64, device=dev)
+    nbytes = lib().dml_ood_workspace_bytes(1, max(n, 1))
+    scratch = ws.get("scan_scratch", nbytes)
+    check(lib().dml_ood_scan_range(C.c_void_p(sorted_keys_ptr), n, ptr(info), recall_level, ptr(scratch), scratch.numel(),
+                                   ptr(partial), stream_ptr(dev)), "dml_ood_scan_range")
+    return partial.cpu().numpy()
+
+
+def combine_partials(partials: Sequence[np.ndarray], total_pos: int, total_n: int):
+    """Combine per-range partial tuples (in ranking order) into (auroc, aupr, fpr, n_groups).
+    Sums are exact integers / fixed-order float64 adds, so every rank computes identical bits."""
+    num = 0
+    ap = 0.0
+    best = (np.inf, -1, 0)
+    groups = 0
+    for p in partials:
+        p = np.asarray(p, dtype=np.int64)
+        num += int(p.view(np.uint64)[0])
+        ap += float(p.view(np.float64)[1])
+        dist, idx, fps = float(p.view(np.float64)[2]), int(p[3]), int(p[4])
+        if dist < best[0] or (dist == best[0] and idx > best[1]):
+            best = (dist, idx, fps)
+        groups += int(p[5])
+    n_neg = total_n - total_pos
+    if total_pos == 0 or n_neg == 0:
+        return float("nan"), float("nan"), float("nan"), groups
+    return num / (2.0 * total_pos * n_neg), ap / total_pos, best[2] / n_neg, groups
+
+
+def measures_from_scores(scores: torch.Tensor, positive: torch.Tensor, recall_level: float = RECALL_LEVEL_DEFAULT,
+                         workspace: Optional[OodWorkspace] = None):
+    """(auroc, aupr, fpr) for arbitrary fp32 scores (higher = more positive) and a 0/1 mask.
+    One segment; the packed-key window is chosen from the data (one extra read of the scores);
+    mixed-sign inputs whose keys span more than 31 bits are ranked as two ranges (score > 0,
+    then score <= 0) that are sorted separately and scanned with carried counts."""
+    require_cuda(scores, "scores")
+    dev = scores.device
+    scores = scores.contiguous().view(-1).float()
+    positive = positive.contiguous().view(-1)
+    if positive.dtype == torch.bool:
+        positive = positive.view(torch.uint8)
+    n = scores.numel()
+    ws = workspace or OodWorkspace(dev)
+    with torch.cuda.device(dev):
+        st = torch.empty(4, dtype=torch.int64, device=dev)
+        check(lib().dml_ood_keystats(ptr(scores), 1, 1, n, ptr(st), stream_ptr(dev)), "dml_ood_keystats")
+        kmin, kmax, n_nan, _ = st.cpu().tolist()
+        if n_nan:
+            raise ValueError("Input contains NaN.")
+        if kmax - kmin < (1 << 31):
+            res, stats = eval_segments(scores, 1, n, positive=positive, score_kind=1, key_base=kmin,
+                                       recall_level=recall_level, workspace=ws)
+            vals, counts = results_to_host(res, stats)
+            return float(vals[0, 0]), float(vals[0, 1]), float(vals[0, 2])
+        # wide, mixed-sign range: keys of positive scores (negative ranking key) come first
+        first = scores > 0
+        parts = [(scores[first], positive[first]), (scores[~first], positive[~first])]
+        total_pos = int(positive.sum().item())
+        partials = []
+        pos_before = idx_before = 0
+        for sc, po in parts:
+            m = sc.numel()
+            if m == 0:
+                continue
+            check(lib().dml_ood_keystats(ptr(sc), 1, 1, m, ptr(st), stream_ptr(dev)), "dml_ood_keystats")
+            base = int(st[0].item())
+            keys = ws.get("keys", 4 * m)
+            stats = ws.get("stats", 32).view(torch.int64)[:4].view(1, 4)
+            check(lib().dml_ood_keygen(ptr(sc), None, 0, None, None, None, 0, ptr(po), 1, base, 1, m, ptr(keys),
+                                       ptr(stats), stream_ptr(dev)), "dml_ood_keygen")
+            nbytes = lib().dml_ood_workspace_bytes(1, m)
+            scratch = ws.get("scratch", nbytes)
+            sorted_ptr = C.c_void_p()
+            check(lib().dml_ood_sort(ptr(keys), 1, m, 0, 32, ptr(scratch), scratch.numel(), C.byref(sorted_ptr),
+                                     stream_ptr(dev)), "dml_ood_sort")
+            _raise_on_bad_stats(stats.cpu().numpy(), "measures_from_scores")
+            partials.append(_scan_sorted_range(sorted_ptr.value, m, pos_before, idx_before, total_pos, n,
+                                               recall_level, ws, dev))
+            pos_before += int(po.sum().item())
+            idx_before += m
+        a, p, f, _ = combine_partials(partials, total_pos, n)
+        return a, p, f

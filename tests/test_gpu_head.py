@@ -1,0 +1,191 @@
+"""Parity of the fused CUDA head (through the C ABI) against the CPU oracle.  GPU only.
+
+Tolerances (north star): labels bit-exact except where the oracle's own top-2 logits are
+within rounding of a tie; distances / EDS within 1e-5 relative (fp32).  Max-softmax: the
+reference evaluates softmax on fp32 logits whose own rounding noise is ~ulp(|z|) in the
+exponent, so the comparison against the fp32 oracle is 1e-5 relative PLUS that conditioning
+term; against the float64 truth the kernel must be within 2e-6.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import dml_oracle as O
+from tests.synth import streethazards_like
+
+pytestmark = pytest.mark.gpu
+
+
+def _near_tie_mask(z: torch.Tensor, rtol=2e-6):
+    """pixels whose best two logits are closer than rounding noise (label may legitimately differ)"""
+    if z.shape[1] < 2:
+        return torch.zeros(z.shape[0], *z.shape[2:], dtype=torch.bool)
+    top2 = torch.topk(z, 2, dim=1).values
+    return (top2[:, 0] - top2[:, 1]).abs() <= rtol * top2[:, 1].abs().clamp_min(1e-30)
+
+
+def _check_head(x_cpu, centers_cpu, K, exclude_back=False, clamp=400.0, dense=False):
+    import dml_b200
+    x = x_cpu.cuda()
+    centers = centers_cpu if not dense else centers_cpu.cuda()
+    out = dml_b200.dml_head(x, centers=centers, want_logits=True, label_dtype=torch.int64, want_maxlogit=True,
+                            want_eds=True, eds_clamp=clamp, want_msp=True, want_minmax=True, exclude_back=exclude_back)
+    torch.cuda.synchronize()
+    z_ref = O.distance_logits(x_cpu, centers_cpu)
+    z64 = O.distance_logits_f64(x_cpu, centers_cpu)
+    z = out.logits.cpu()
+    # distances: 1e-5 relative vs the fp32 oracle, tighter vs float64 truth
+    np.testing.assert_allclose(z.numpy(), z_ref.numpy(), rtol=1e-5, atol=0)
+    np.testing.assert_allclose(z.numpy(), z64.numpy(), rtol=3e-6, atol=0)
+    # labels
+    lab = out.label.cpu()
+    ref_lab = z_ref.max(dim=1)[1]
+    diff = lab != ref_lab
+    assert not (diff & ~_near_tie_mask(z_ref)).any(), "label mismatch away from ties"
+    assert torch.equal(lab, z.max(dim=1)[1]), "labels must be the argmax of the logits the kernel wrote"
+    # scores
+    first = 1 if exclude_back else 0
+    zs = z_ref[:, first:]
+    eds_ref = -(zs.sum(dim=1))
+    eds_ref = torch.where(eds_ref >= clamp, torch.full_like(eds_ref, clamp), eds_ref) if clamp > 0 else eds_ref
+    np.testing.assert_allclose(out.eds.cpu().numpy(), eds_ref.numpy(), rtol=1e-5)
+    np.testing.assert_allclose(out.maxlogit.cpu().numpy(), zs.max(dim=1)[0].numpy(), rtol=1e-5)
+    msp_ref = torch.softmax(zs, dim=1).max(dim=1)[0]
+    msp64 = torch.softmax(z64[:, first:], dim=1).max(dim=1)[0]
+    msp = out.msp.cpu()
+    np.testing.assert_allclose(msp.numpy(), msp64.numpy(), rtol=2e-6)
+    cond = 4 * np.spacing(np.float32(zs.abs().max().item()))
+    np.testing.assert_allclose(msp.numpy(), msp_ref.numpy(), rtol=1e-5, atol=float(cond))
+    # per-image min / max are exactly the min / max of the maps the kernel wrote
+    mm = out.minmax.cpu()
+    B = x.shape[0]
+    e, m = out.eds.cpu().view(B, -1), msp.view(B, -1)
+    assert torch.equal(mm[:, 0], e.min(1)[0]) and torch.equal(mm[:, 1], e.max(1)[0])
+    assert torch.equal(mm[:, 2], m.min(1)[0]) and torch.equal(mm[:, 3], m.max(1)[0])
+    return out
+
+
+@pytest.mark.parametrize("k,h,w", [(13, 72, 128), (16, 64, 96), (17, 48, 64), (19, 40, 52), (13, 38, 67), (3, 9, 7), (1, 5, 4),
+                                   (32, 16, 24), (24, 20, 20)])
+def test_head_identity_prototypes(k, h, w):
+    x, _ = streethazards_like(2, h, w, k=k, sigma=0.7, ood_label=k, seed=k + h)
+    _check_head(x, O.make_centers(k), k)
+
+
+def test_head_tight_clusters_no_cancellation():
+    """sigma = 0.1 puts own-class distances at ~0.03..0.1 while ||x||^2 ~ 9: an expanded-form kernel
+    loses 1e-4 relative here (hard part 2); the leave-one-out form must not."""
+    x, _ = streethazards_like(2, 64, 64, k=13, sigma=0.1, seed=5)
+    _check_head(x, O.make_centers(13), 13)
+
+
+def test_head_exclude_back_and_no_clamp():
+    x, _ = streethazards_like(1, 40, 64, k=13, seed=9)
+    _check_head(x, O.make_centers(13), 13, exclude_back=True, clamp=0.0)
+
+
+@pytest.mark.parametrize("k,d", [(16, 16), (17, 16), (5, 13), (13, 19)])
+def test_head_dense_prototypes(k, d):
+    g = torch.Generator().manual_seed(k * 100 + d)
+    centers = torch.randn(k, d, generator=g) * 2
+    x = centers[torch.randint(0, k, (2, 24, 40), generator=g)].permute(0, 3, 1, 2).contiguous()
+    x = x + 0.5 * torch.randn(x.shape, generator=g)
+    _check_head(x, centers, k, dense=True)
+
+
+def test_head_golden_deeplab(golden):
+    """logits / NHWC features / centers against values captured from the reference model."""
+    import dml_b200
+    g = golden("head_deeplab.npz")
+    for k in (16, 17, 19):
+        feats = torch.from_numpy(g[f"k{k}_features_nhwc"])
+        x = feats.permute(0, 3, 1, 2).contiguous().cuda()
+        out = dml_b200.dml_head(x, want_logits=True, want_features=True, label_dtype=torch.int64)
+        np.testing.assert_allclose(out.logits.cpu().numpy(), g[f"k{k}_logits"], rtol=1e-5)
+        assert torch.equal(out.features.cpu(), feats)
+        ref = torch.from_numpy(g[f"k{k}_logits"])
+        diff = out.label.cpu() != ref.max(dim=1)[1]
+        assert not (diff & ~_near_tie_mask(ref)).any()
+
+
+def test_head_golden_anomaly_lowres(golden):
+    import dml_b200
+    g = golden("head_anomaly.npz")
+    for tag in ("a", "b"):
+        x = torch.from_numpy(g[f"{tag}_x_low"]).cuda()
+        out = dml_b200.dml_head(x, centers=torch.from_numpy(g[f"{tag}_centers"]), want_logits=True)
+        np.testing.assert_allclose(out.logits.cpu().numpy(), g[f"{tag}_z_low"], rtol=1e-5)
+
+
+def test_head_logits_mode_matches_reference_scores(golden):
+    """anomaly path: scores from already-averaged logits (eval_ood_traditional.py:218,302-305)."""
+    import dml_b200
+    g = golden("evaluate_anomaly.npz")
+    c = O.make_centers(13)
+    for i in range(2):
+        lows = [torch.from_numpy(g[f"img{i}_low{s}"]) for s in range(5)]
+        seg = g[f"img{i}_seg"]
+        scores, _ = O.multiscale_scores(lows, c, seg.shape)
+        out = dml_b200.dml_head(scores.cuda(), input_is_logits=True, label_dtype=torch.int64, want_eds=True,
+                                eds_clamp=400.0, want_msp=True, want_minmax=True)
+        assert np.array_equal(out.label.cpu().numpy()[0], g[f"img{i}_pred"])
+        eds_n, msp_n, mix = dml_b200.finalize_scores(out.eds, out.msp, out.minmax, want_msp=True, want_mix=True)
+        np.testing.assert_allclose(eds_n.cpu().numpy()[0], g[f"img{i}_conf"], rtol=1e-5, atol=1e-7)
+        np.testing.assert_allclose(msp_n.cpu().numpy()[0], O.score_mmsp(scores), rtol=1e-5, atol=2e-6)
+        np.testing.assert_allclose(mix.cpu().numpy()[0], O.score_mix(O.score_dissum(scores), O.score_mmsp(scores)),
+                                   rtol=1e-5, atol=3e-6)
+
+
+def test_head_npm_and_confusion(golden):
+    """NPM override (float64 novel distance) + fused 19x19 confusion vs the reference's validate()."""
+    import dml_b200
+    g = golden("validate_deeplab.npz")
+    proto = torch.from_numpy(O.novel_prototype(g["prototypes"].tolist())).view(1, 16)
+    conf = torch.zeros(19, 19, dtype=torch.int64, device="cuda")
+    for i in range(3):
+        feats = torch.from_numpy(g[f"img{i}_features_nhwc"])
+        x = feats.permute(0, 3, 1, 2).contiguous().cuda()
+        targets = torch.from_numpy(g[f"img{i}_targets"]).cuda()
+        out = dml_b200.dml_head(x, want_logits=True, label_dtype=torch.int64, novel=proto, novel_label_base=16,
+                                novel_thr=-1.5, want_novel_dist=True, gt=targets, confusion=conf)
+        ref_preds = torch.from_numpy(g[f"img{i}_preds"])
+        logits_ref = torch.from_numpy(g[f"img{i}_logits"])
+        preds0, dis = O.npm_override(O.argmax_label(logits_ref), logits_ref, feats, proto.numpy()[0])
+        np.testing.assert_array_equal(out.novel_dist.cpu().numpy()[0, 0], dis)   # float64, NumPy summation order
+        assert torch.equal(out.label.cpu(), ref_preds)
+    np.testing.assert_array_equal(conf.cpu().numpy(), g["confusion"].astype(np.int64))
+
+
+def test_confusion_and_plm_merge(golden):
+    import dml_b200
+    g = golden("segmetrics.npz")
+    conf = torch.zeros(19, 19, dtype=torch.int64, device="cuda")
+    for gt, pr in zip(g["dl_gt"], g["dl_pred"]):
+        dml_b200.confusion_counts(torch.from_numpy(gt).cuda(), torch.from_numpy(pr).cuda(), 19, 19, out=conf)
+    np.testing.assert_array_equal(conf.cpu().numpy(), g["dl_confusion"].astype(np.int64))
+    # uint8 labels take the same path
+    conf8 = dml_b200.confusion_counts(torch.from_numpy(g["dl_gt"][0]).to(torch.uint8).cuda(),
+                                      torch.from_numpy(g["dl_pred"][0]).to(torch.uint8).cuda(), 19, 19)
+    conf64 = dml_b200.confusion_counts(torch.from_numpy(g["dl_gt"][0]).cuda(), torch.from_numpy(g["dl_pred"][0]).cuda(), 19, 19)
+    assert torch.equal(conf8, conf64)
+    p = golden("plm.npz")
+    outs = []
+    for i, k in enumerate((16, 17)):
+        x = torch.from_numpy(p[f"head{i}_features_nhwc"]).permute(0, 3, 1, 2).contiguous().cuda()
+        outs.append(dml_b200.dml_head(x, want_logits=False, label_dtype=torch.int64).label)
+    merged = dml_b200.plm_merge(outs[0].clone(), outs[1], 16)
+    np.testing.assert_array_equal(merged.cpu().numpy(), p["merged_preds"])
+
+
+def test_head_rejects_cpu_tensor_and_bad_dim():
+    import dml_b200
+    with pytest.raises(dml_b200.DmlError):
+        dml_b200.dml_head(torch.zeros(1, 13, 4, 4))
+    with pytest.raises(dml_b200.DmlError):
+        dml_b200.dml_head(torch.zeros(1, 40, 4, 4, device="cuda"))
+
+
+def test_head_empty_batch():
+    import dml_b200
+    out = dml_b200.dml_head(torch.zeros(0, 13, 8, 8, device="cuda"), want_eds=True)
+    assert out.logits.shape == (0, 13, 8, 8) and out.eds.shape == (0, 8, 8)
