@@ -51,6 +51,8 @@ DML_API const char* dml_error_string(int code);
 DML_API int dml_last_cuda_error(void);
 /* Largest supported embedding dim D and class count K (compile-time unrolled kernels). */
 DML_API int dml_max_dim(void);
+/* Number of CUDA kernels this library has enqueued so far in this process (benchmark bookkeeping). */
+DML_API unsigned long long dml_kernel_launches(void);
 
 /* ------------------------------------------------------------------------------------ *
  * (a) Fused distance + score head.

@@ -53,6 +53,7 @@ SIGNATURES = {
     "dml_error_string": (C.c_char_p, [C.c_int]),
     "dml_last_cuda_error": (C.c_int, []),
     "dml_max_dim": (C.c_int, []),
+    "dml_kernel_launches": (C.c_ulonglong, []),
     "dml_head_forward": (C.c_int, [C.POINTER(HeadParams), C.c_void_p]),
     "dml_scores_finalize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_float,
                                       C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

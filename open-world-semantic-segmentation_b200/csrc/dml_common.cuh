@@ -9,6 +9,7 @@
 namespace dml {
 
 extern thread_local int g_last_cuda_error;
+extern unsigned long long g_kernel_launches;  // kernels enqueued by this library (bench bookkeeping; racy by design)
 
 inline int cuda_fail(cudaError_t e) {
   g_last_cuda_error = (int)e;
@@ -21,7 +22,11 @@ inline int cuda_fail(cudaError_t e) {
     if (_e != cudaSuccess) return ::dml::cuda_fail(_e);      \
   } while (0)
 
-#define DML_LAUNCH_CHECK() DML_CUDA_TRY(cudaGetLastError())
+#define DML_LAUNCH_CHECK()                 \
+  do {                                     \
+    ++::dml::g_kernel_launches;            \
+    DML_CUDA_TRY(cudaGetLastError());      \
+  } while (0)
 
 static inline int ceil_div_i(long long a, long long b) { return (int)((a + b - 1) / b); }
 

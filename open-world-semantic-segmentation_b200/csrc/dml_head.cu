@@ -5,6 +5,7 @@
 namespace dml {
 
 thread_local int g_last_cuda_error = 0;
+unsigned long long g_kernel_launches = 0;
 
 __global__ void minmax_init_kernel(int* mm, int n4) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -95,6 +96,7 @@ extern "C" {
 int dml_abi_version(void) { return DML_B200_ABI_VERSION; }
 int dml_max_dim(void) { return DML_MAX_DIM; }
 int dml_last_cuda_error(void) { return g_last_cuda_error; }
+unsigned long long dml_kernel_launches(void) { return g_kernel_launches; }
 
 const char* dml_error_string(int code) {
   switch (code) {

@@ -167,7 +167,8 @@ def dml_head(x: torch.Tensor, centers: Optional[torch.Tensor] = None, magnitude:
 
 def finalize_scores(eds: Optional[torch.Tensor], msp: Optional[torch.Tensor], minmax: torch.Tensor, *,
                     want_eds: bool = True, want_msp: bool = False, want_mix: bool = False, lam: float = 50.0,
-                    thr: float = 0.2, complement: bool = False):
+                    thr: float = 0.2, complement: bool = False, out_eds: Optional[torch.Tensor] = None,
+                    out_msp: Optional[torch.Tensor] = None, out_mix: Optional[torch.Tensor] = None):
     """Per-image min-max normalisation (+ EDS/MMSP mix) of raw score maps [B,H,W]
     (anomaly/eval_ood_traditional.py:101-106,305,435,447-448).  Returns (eds_n, msp_n, mix)."""
     ref = eds if eds is not None else msp
@@ -175,9 +176,9 @@ def finalize_scores(eds: Optional[torch.Tensor], msp: Optional[torch.Tensor], mi
     B = ref.shape[0]
     hw = ref[0].numel()
     dev = ref.device
-    eds_n = torch.empty_like(eds) if (want_eds and eds is not None) else None
-    msp_n = torch.empty_like(msp) if (want_msp and msp is not None) else None
-    mix = torch.empty_like(eds) if want_mix else None
+    eds_n = (out_eds if out_eds is not None else torch.empty_like(eds)) if (want_eds and eds is not None) else None
+    msp_n = (out_msp if out_msp is not None else torch.empty_like(msp)) if (want_msp and msp is not None) else None
+    mix = (out_mix if out_mix is not None else torch.empty_like(eds)) if want_mix else None
     with torch.cuda.device(dev):
         check(lib().dml_scores_finalize(ptr(eds), ptr(msp), ptr(minmax), B, hw, lam, thr, 1 if complement else 0,
                                         ptr(eds_n), ptr(msp_n), ptr(mix), stream_ptr(dev)), "dml_scores_finalize")
