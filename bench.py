@@ -293,11 +293,11 @@ class Pipeline:
             ev1.record()
             self.head_events.append((ev0, ev1))
         nb = e - s
-        H.finalize_scores(self.eds[s:e], self.msp[s:e], self.minmax[s:e], want_eds=False, want_msp=True, want_mix=True,
-                          out_msp=self.mmsp_c[:nb], out_mix=self.mix_c[:nb])
+        # key-gen reads the raw EDS once: normalised conf map, MMSP map, mix map and ranking keys
         res, stats = ood.eval_segments(self.eds[s:e], nb, self.hw, gt=gt, out_labels=(self.k,), score_kind=0,
                                        minmax=self.minmax[s:e], minmax_slot=0, conf_out=self.conf[s:e],
-                                       workspace=self.ws_img)
+                                       workspace=self.ws_img, msp=self.msp[s:e], msp_norm_out=self.mmsp_c[:nb],
+                                       mix_out=self.mix_c[:nb])
         self.per_image[s:e].copy_(res)
         self.per_image_stats[s:e].copy_(stats)
 

@@ -200,11 +200,15 @@ DML_API int dml_ood_keystats(const float* values, int32_t score_kind, int32_t n_
  * Packed key = ((sortable(key) - key_base) << 1) | positive; all keys of a call must lie in
  * [key_base, key_base + 2^31) -- true with key_base = 0x80000000 for any non-negative conf
  * (e.g. normalised maps in [0,1]); violations are counted, not silently wrapped.
- * seg_stats (device, [n_seg,4] int64) = (n_pos, n_nan, n_out_of_window, 0). */
+ * seg_stats (device, [n_seg,4] int64) = (n_pos, n_nan, n_out_of_window, 0).
+ * Optional fused score outputs (need minmax, minmax_slot == 0): with `msp` = raw max-softmax map,
+ * `msp_norm_out` = its min-max normalisation (MMSP, eval_ood_traditional.py:434-435) and `mix_out` =
+ * c*eds_n + (1-c)*mmsp with c = 1/(1+exp(lambda (eds_n - thr))) (:104-106,447-448). */
 DML_API int dml_ood_keygen(const float* values, const float* minmax, int32_t minmax_slot, float* conf_out,
                    const uint8_t* gt_u8, const int64_t* gt_i64, uint64_t out_label_mask,
                    const uint8_t* pos_u8, int32_t score_kind, uint32_t key_base, int32_t n_seg,
-                   int64_t seg_len, uint32_t* keys, long long* seg_stats, dml_stream_t stream);
+                   int64_t seg_len, uint32_t* keys, long long* seg_stats, const float* msp,
+                   float* msp_norm_out, float* mix_out, float lambda, float thr, dml_stream_t stream);
 
 DML_API size_t dml_ood_workspace_bytes(int32_t n_seg, int64_t seg_len);
 /* Sort `keys` (n_seg segments of seg_len packed keys; clobbered) and evaluate every segment.

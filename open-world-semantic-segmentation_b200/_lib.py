@@ -73,7 +73,7 @@ SIGNATURES = {
     "dml_ood_keystats": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p]),
     "dml_ood_keygen": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64,
                                  C.c_void_p, C.c_int32, C.c_uint32, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p,
-                                 C.c_void_p]),
+                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p]),
     "dml_ood_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int64]),
     "dml_ood_eval_segments": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_double, C.c_void_p,
                                         C.c_size_t, C.c_void_p, C.c_void_p]),

@@ -1,5 +1,6 @@
 // C-ABI entry points of the head path: dml_head_forward, dml_scores_finalize, dml_confusion,
 // dml_plm_merge, plus library-level helpers.  Kernel body lives in dml_head.cuh.
+#include <cstdlib>
 #include "dml_head.cuh"
 
 namespace dml {
@@ -74,11 +75,16 @@ __global__ void __launch_bounds__(256) plm_merge_kernel(T* base, const T* __rest
 
 static int pick_vec(const dml_head_params* p, long long hw) {
   auto al = [](const void* q, size_t a) { return q == nullptr || (reinterpret_cast<uintptr_t>(q) % a) == 0; };
-  for (int vec = 4; vec >= 2; vec >>= 1) {
+  int vmax = 4;
+  if (const char* e = getenv("DML_HEAD_VEC")) {  // tuning knob: cap the pixels per thread
+    const int v = atoi(e);
+    if (v == 1 || v == 2 || v == 4) vmax = v;
+  }
+  for (int vec = vmax; vec >= 2; vec >>= 1) {
     if (hw % vec) continue;
     const size_t fa = 4 * (size_t)vec;
     if (!al(p->x, fa) || !al(p->logits, fa) || !al(p->maxlogit, fa) || !al(p->eds, fa) || !al(p->msp, fa)) continue;
-    if (!al(p->label_u8, vec) || !al(p->label_i64, 16)) continue;
+    if (!al(p->label_u8, vec) || !al(p->label_i64, 16) || !al(p->gt_u8, vec)) continue;
     // very wide embeddings: keep the register footprint (D * VEC floats) bounded
     if (p->D * vec > 96) continue;
     return vec;
@@ -119,7 +125,7 @@ int dml_head_forward(const dml_head_params* p, dml_stream_t stream_) {
   const int mode = p->input_is_logits ? HEAD_LOGITS : (p->mu == nullptr ? HEAD_IDENT : HEAD_DENSE);
   if (mode != HEAD_DENSE && p->K != p->D) return DML_ERR_INVALID_ARG;
   if (mode == HEAD_LOGITS && (p->mu || p->n_novel > 0 || p->features_nhwc || p->logits || p->novel_dist)) return DML_ERR_INVALID_ARG;
-  if (p->score_first_class < 0 || p->score_first_class >= p->K) return DML_ERR_INVALID_ARG;
+  if (p->score_first_class < 0 || p->score_first_class > 1 || p->score_first_class >= p->K) return DML_ERR_INVALID_ARG;
   if (p->n_novel < 0 || p->n_novel > HEAD_MAX_NOVEL || (p->n_novel > 0 && !p->mu_novel)) return DML_ERR_INVALID_ARG;
   if (p->n_novel > 0 && p->novel_label_base + p->n_novel > 256) return DML_ERR_INVALID_ARG;
   if ((p->want_eds_minmax || p->want_msp_minmax) && !p->minmax) return DML_ERR_INVALID_ARG;
@@ -149,7 +155,7 @@ int dml_head_forward(const dml_head_params* p, dml_stream_t stream_) {
     minmax_init_kernel<<<ceil_div_i(n4, 256), 256, 0, stream>>>(a.minmax, n4);
     DML_LAUNCH_CHECK();
   }
-  const bool extra = a.n_novel > 0 || a.feat != nullptr || a.novel_dist != nullptr;
+  const bool extra = a.n_novel > 0 || a.feat != nullptr || a.novel_dist != nullptr || a.logits != nullptr;
   int vec = pick_vec(p, hw);
   if (extra && vec > 2) vec = 2;
   const int D = p->D;

@@ -89,13 +89,32 @@ __device__ __forceinline__ double novel_neg_dist(const float (&x)[D][VEC], int v
   return -res;
 }
 
-// EXTRA = the rarely used outputs that keep x[][] live to the end and need fp64 (NPM novel prototypes,
-// novel_dist, NHWC feature copy); compiled separately so the lean scoring path keeps a small register file.
+// Adds one observation to a block-shared histogram with a single shared-memory update per distinct
+// bin in the warp (segmentation labels are spatially coherent: usually 1-3 distinct bins per warp).
+__device__ __forceinline__ void warp_histogram_add(unsigned int* s_bins, int bin) {
+  unsigned todo = __ballot_sync(0xffffffffu, bin >= 0);
+  const int lane = threadIdx.x & 31;
+  while (todo) {
+    const int leader = __ffs(todo) - 1;
+    const int b = __shfl_sync(0xffffffffu, bin, leader);
+    const unsigned members = __ballot_sync(0xffffffffu, bin == b);
+    if (lane == leader) atomicAdd(&s_bins[b], (unsigned)__popc(members));
+    todo &= ~members;
+  }
+}
+
+// EXTRA = the outputs that keep x[][] live to the end or need fp64 / per-class stores (distance
+// logits, NPM novel prototypes, novel_dist, NHWC feature copy); compiled separately so that the lean
+// scoring path (labels + EDS + MSP + min/max + confusion) keeps a short instruction stream and a
+// small register file.  `skip0` (OOD.exclude_back) only ever removes class 0 from the SCORES, so it
+// costs one uniform select on the k = 0 terms instead of a predicate per class.
 template <int D, int MODE, int VEC, bool EXTRA>
 __global__ void __launch_bounds__(HEAD_THREADS) head_kernel(const HeadArgs a) {
   constexpr bool IDENT = (MODE == HEAD_IDENT);
   constexpr bool LOGITS = (MODE == HEAD_LOGITS);
   constexpr bool DENSE = (MODE == HEAD_DENSE);
+  constexpr float LOG2E = 1.4426950408889634f;
+  constexpr float PINF = __builtin_huge_valf();
   extern __shared__ __align__(16) unsigned char smem_dyn[];
   __shared__ int s_red[4][HEAD_THREADS / 32];
 
@@ -108,7 +127,8 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_kernel(const HeadArgs a) {
   const int K = DENSE ? a.K : D;
   const int nbins = a.conf ? a.crow * a.ccol : 0;
 
-  for (int i = threadIdx.x; i < n_novel * D; i += HEAD_THREADS) s_novel[i] = a.mu_novel[i];
+  if constexpr (EXTRA)
+    for (int i = threadIdx.x; i < n_novel * D; i += HEAD_THREADS) s_novel[i] = a.mu_novel[i];
   if constexpr (DENSE) {
     for (int i = threadIdx.x; i < K * DP; i += HEAD_THREADS) {
       int k = i / DP, d = i - k * DP;
@@ -116,13 +136,14 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_kernel(const HeadArgs a) {
     }
   }
   for (int i = threadIdx.x; i < nbins; i += HEAD_THREADS) s_conf[i] = 0u;
-  const bool need_sync = (n_novel > 0) || DENSE || nbins > 0;
-  if (need_sync) __syncthreads();
+  if ((EXTRA && n_novel > 0) || DENSE || nbins > 0) __syncthreads();
 
   const int b = blockIdx.y;
   const long long p0 = ((long long)blockIdx.x * HEAD_THREADS + threadIdx.x) * VEC;
   const bool active = p0 < a.HW;
   const uint64_t pol = policy_evict_first();
+  const bool skip0 = a.first != 0;
+  const bool want_msp = (a.msp != nullptr) || a.want_msp_mm;
 
   float x[D][VEC];
   {
@@ -141,18 +162,22 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_kernel(const HeadArgs a) {
     }
   }
 
-  float dmin[VEC], smin[VEC], eds[VEC], ssum[VEC];
-  int arg[VEC];
+  // per pixel: d0 = distance to class 0; (dmin1, arg1) = best of classes >= 1; esum1 = sum over classes >= 1
+  float d0[VEC], dmin1[VEC], esum1[VEC], ssum[VEC];
+  int arg1[VEC];
 #pragma unroll
-  for (int v = 0; v < VEC; ++v) {
-    dmin[v] = __int_as_float(0x7f800000);
-    smin[v] = __int_as_float(0x7f800000);
-    eds[v] = 0.f;
-    ssum[v] = 0.f;
-    arg[v] = 0;
-  }
-  const bool want_msp = (a.msp != nullptr) || a.want_msp_mm;
-  float* lg = (a.logits && !LOGITS) ? a.logits + ((long long)b * K) * a.HW + p0 : nullptr;
+  for (int v = 0; v < VEC; ++v) { d0[v] = 0.f; dmin1[v] = PINF; esum1[v] = 0.f; ssum[v] = 0.f; arg1[v] = 0; }
+  float* lg = nullptr;
+  if constexpr (EXTRA && !LOGITS) lg = a.logits ? a.logits + ((long long)b * K) * a.HW + p0 : nullptr;
+
+  auto visit = [&](int k, int v, float dk) {
+    if (k == 0) {
+      d0[v] = dk;
+    } else {
+      if (dk < dmin1[v]) { dmin1[v] = dk; arg1[v] = k; }
+      esum1[v] += dk;
+    }
+  };
 
   if constexpr (IDENT) {
     // d_k = sum_{d != k} x_d^2 + (x_k - m)^2.  The leave-one-out sum of squares is assembled
@@ -185,19 +210,6 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_kernel(const HeadArgs a) {
         for (int j = 0; j < NG; ++j) outer[j][v] = pre[j] + suf[j];
       }
     }
-    // softmax_k(z) == softmax_k(2 m x_k) when mu = m I (z_k - z_j = 2 m (x_k - x_j) exactly), so the
-    // max-softmax is 1 / sum_k exp(2m (x_k - x_ext)) with x_ext the max (m > 0) or min (m < 0) of x.
-    float xext[VEC];
-    if (want_msp) {
-#pragma unroll
-      for (int v = 0; v < VEC; ++v) {
-        float t = a.msp_scale >= 0.f ? __int_as_float(0xff800000) : __int_as_float(0x7f800000);
-#pragma unroll
-        for (int k = 0; k < D; ++k)
-          if (k >= a.first) t = a.msp_scale >= 0.f ? fmaxf(t, x[k][v]) : fminf(t, x[k][v]);
-        xext[v] = t;
-      }
-    }
 #pragma unroll
     for (int k = 0; k < D; ++k) {
       const int j = k >> 2;
@@ -212,46 +224,53 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_kernel(const HeadArgs a) {
         }
         const float t = x[k][v] - a.diag_m;
         const float dk = fmaf(t, t, r);
-        if (dk < dmin[v]) { dmin[v] = dk; arg[v] = k; }
-        if (k >= a.first) {
-          smin[v] = fminf(smin[v], dk);
-          eds[v] += dk;
-          if (want_msp) ssum[v] += ex2_approx(a.msp_scale * (x[k][v] - xext[v]));
-        }
+        visit(k, v, dk);
         z.v[v] = -dk;
       }
-      if (lg && active) st_stream<VEC>(lg + (long long)k * a.HW, z);
+      if constexpr (EXTRA)
+        if (lg && active) st_stream<VEC>(lg + (long long)k * a.HW, z);
+    }
+    // softmax_k(z) == softmax_k(2 m x_k) when mu = m I (z_k - z_j = 2 m (x_k - x_j) exactly), so the
+    // max-softmax is 1 / sum_k exp2(c x_k - c x_ext), c = 2 m log2(e), x_ext the max (m > 0) / min (m < 0).
+    if (want_msp) {
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) {
+        const float c = a.msp_scale;
+        float ext = skip0 ? x[D > 1 ? 1 : 0][v] : x[0][v];
+#pragma unroll
+        for (int k = 1; k < D; ++k) ext = c >= 0.f ? fmaxf(ext, x[k][v]) : fminf(ext, x[k][v]);
+        const float off = -c * ext;
+        float s = skip0 ? 0.f : ex2_approx(fmaf(c, x[0][v], off));
+#pragma unroll
+        for (int k = 1; k < D; ++k) s += ex2_approx(fmaf(c, x[k][v], off));
+        ssum[v] = s;
+      }
     }
   } else if constexpr (LOGITS) {
     // input channels ARE the logits z_k (anomaly path: distances taken at stride 8, then upsampled
     // and averaged over scales by the caller, anomaly/eval_ood_traditional.py:198-210): d_k = -z_k
-    constexpr float LOG2E = 1.4426950408889634f;
-    float zmax[VEC];
 #pragma unroll
-    for (int v = 0; v < VEC; ++v) {
-      float t = __int_as_float(0xff800000);
+    for (int k = 0; k < D; ++k)
 #pragma unroll
-      for (int k = 0; k < D; ++k)
-        if (k >= a.first) t = fmaxf(t, x[k][v]);
-      zmax[v] = t;
-    }
-#pragma unroll
-    for (int k = 0; k < D; ++k) {
+      for (int v = 0; v < VEC; ++v) visit(k, v, -x[k][v]);
+    if (want_msp) {
 #pragma unroll
       for (int v = 0; v < VEC; ++v) {
-        const float dk = -x[k][v];
-        if (dk < dmin[v]) { dmin[v] = dk; arg[v] = k; }
-        if (k >= a.first) {
-          eds[v] += dk;
-          if (want_msp) ssum[v] += ex2_approx((x[k][v] - zmax[v]) * LOG2E);
-        }
+        float zmax = skip0 ? x[D > 1 ? 1 : 0][v] : x[0][v];
+#pragma unroll
+        for (int k = 1; k < D; ++k) zmax = fmaxf(zmax, x[k][v]);
+        float s = skip0 ? 0.f : ex2_approx((x[0][v] - zmax) * LOG2E);
+#pragma unroll
+        for (int k = 1; k < D; ++k) s += ex2_approx((x[k][v] - zmax) * LOG2E);
+        ssum[v] = s;
       }
     }
-#pragma unroll
-    for (int v = 0; v < VEC; ++v) smin[v] = -zmax[v];
   } else {
-    // dense prototypes: direct form, prototypes broadcast from shared memory; online softmax
-    constexpr float LOG2E = 1.4426950408889634f;
+    // dense prototypes: direct form, prototypes broadcast from shared memory; online softmax over the
+    // score classes (running minimum distance mrun, running sum of exp(-(d_k - mrun)))
+    float mrun[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) mrun[v] = PINF;
     for (int k = 0; k < K; ++k) {
       const float4* mrow = reinterpret_cast<const float4*>(s_mu + k * DP);
       float acc[VEC];
@@ -277,31 +296,33 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_kernel(const HeadArgs a) {
 #pragma unroll
       for (int v = 0; v < VEC; ++v) {
         const float dk = acc[v];
-        if (dk < dmin[v]) { dmin[v] = dk; arg[v] = k; }
-        if (k >= a.first) {
-          if (want_msp) {
-            const float nm = fminf(smin[v], dk);
-            // sum_k exp(-(d_k - dmin)) maintained online
-            ssum[v] = ssum[v] * ex2_approx((nm - smin[v]) * LOG2E) + ex2_approx((nm - dk) * LOG2E);
-            smin[v] = nm;
-          } else {
-            smin[v] = fminf(smin[v], dk);
-          }
-          eds[v] += dk;
+        visit(k, v, dk);
+        if (want_msp && (k > 0 || !skip0)) {
+          const float nm = fminf(mrun[v], dk);
+          ssum[v] = ssum[v] * ex2_approx((nm - mrun[v]) * LOG2E) + ex2_approx((nm - dk) * LOG2E);
+          mrun[v] = nm;
         }
         z.v[v] = -dk;
       }
-      if (lg && active) st_stream<VEC>(lg + (long long)k * a.HW, z);
+      if constexpr (EXTRA)
+        if (lg && active) st_stream<VEC>(lg + (long long)k * a.HW, z);
     }
   }
 
   // ---- per-pixel results ---------------------------------------------------------------
+  // label = argmin over ALL classes (first minimum wins, like torch.max on the logits);
+  // scores (eds, maxlogit, msp) over the score classes (all, or all but class 0)
   int label[VEC];
-  float mspv[VEC];
+  float dbest[VEC], smin[VEC], eds[VEC], mspv[VEC];
 #pragma unroll
   for (int v = 0; v < VEC; ++v) {
-    label[v] = arg[v];
-    if (a.clamp > 0.f) eds[v] = (eds[v] >= a.clamp) ? a.clamp : eds[v];
+    const bool zero_wins = (K == 1) || !(dmin1[v] < d0[v]);
+    label[v] = zero_wins ? 0 : arg1[v];
+    dbest[v] = zero_wins ? d0[v] : dmin1[v];
+    smin[v] = (skip0 && K > 1) ? dmin1[v] : dbest[v];
+    float e = (skip0 && K > 1) ? esum1[v] : d0[v] + esum1[v];
+    if (a.clamp > 0.f) e = (e >= a.clamp) ? a.clamp : e;
+    eds[v] = e;
     mspv[v] = want_msp ? (1.0f / ssum[v]) : 0.f;
   }
 
@@ -312,7 +333,7 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_kernel(const HeadArgs a) {
 #pragma unroll
       for (int v = 0; v < VEC; ++v) {
         const double zn = novel_neg_dist<D, VEC>(x, v, s_novel + j * D);
-        const double zmax = (double)(-dmin[v]);
+        const double zmax = (double)(-dbest[v]);
         if (zn > a.novel_thr && zn > zmax) label[v] = a.novel_base + j;
         if (a.novel_dist && active)
           a.novel_dist[((long long)j * a.B + b) * a.HW + p0 + v] = zn;
@@ -380,8 +401,8 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_kernel(const HeadArgs a) {
         mmin = min(mmin, m); mmax = max(mmax, m);
       }
     }
-    emin = warp_reduce_min_i(emin); emax = warp_reduce_max_i(emax);
-    mmin = warp_reduce_min_i(mmin); mmax = warp_reduce_max_i(mmax);
+    emin = __reduce_min_sync(0xffffffffu, emin); emax = __reduce_max_sync(0xffffffffu, emax);
+    mmin = __reduce_min_sync(0xffffffffu, mmin); mmax = __reduce_max_sync(0xffffffffu, mmax);
     const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
     if (l == 0) { s_red[0][w] = emin; s_red[1][w] = emax; s_red[2][w] = mmin; s_red[3][w] = mmax; }
     __syncthreads();
@@ -400,16 +421,34 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_kernel(const HeadArgs a) {
 
   // ---- fused confusion counts -------------------------------------------------------------
   if (nbins > 0) {
+    int bin[VEC];
 #pragma unroll
-    for (int v = 0; v < VEC; ++v) {
-      int bin = -1;
-      if (active) {
-        const long long g = a.gt_u8 ? (long long)a.gt_u8[pix + v] : a.gt_i64[pix + v];
-        if (g >= 0 && g < a.crow && label[v] < a.ccol) bin = (int)g * a.ccol + label[v];
+    for (int v = 0; v < VEC; ++v) bin[v] = -1;
+    if (active) {
+      if (a.gt_u8) {
+        unsigned char g[VEC];
+        if constexpr (VEC == 4) {
+          const uchar4 t = *reinterpret_cast<const uchar4*>(a.gt_u8 + pix);
+          g[0] = t.x; g[1] = t.y; g[2] = t.z; g[3] = t.w;
+        } else if constexpr (VEC == 2) {
+          const uchar2 t = *reinterpret_cast<const uchar2*>(a.gt_u8 + pix);
+          g[0] = t.x; g[1] = t.y;
+        } else {
+          g[0] = a.gt_u8[pix];
+        }
+#pragma unroll
+        for (int v = 0; v < VEC; ++v)
+          if ((int)g[v] < a.crow && label[v] < a.ccol) bin[v] = (int)g[v] * a.ccol + label[v];
+      } else {
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+          const long long g = a.gt_i64[pix + v];
+          if (g >= 0 && g < a.crow && label[v] < a.ccol) bin[v] = (int)g * a.ccol + label[v];
+        }
       }
-      const unsigned peers = __match_any_sync(0xffffffffu, bin);
-      if (bin >= 0 && (threadIdx.x & 31) == (__ffs(peers) - 1)) atomicAdd(&s_conf[bin], (unsigned)__popc(peers));
     }
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) warp_histogram_add(s_conf, bin[v]);
     __syncthreads();
     for (int i = threadIdx.x; i < nbins; i += HEAD_THREADS) {
       const unsigned c = s_conf[i];

@@ -52,37 +52,97 @@ __device__ __forceinline__ bool is_positive(const GT* gt, const uint8_t* pos_u8,
   return g >= 0 && g < 64 && ((mask >> g) & 1ull);
 }
 
-template <typename GT>
+// Optional extra outputs of key generation: the normalised max-softmax map (MMSP) and the
+// EDS/MMSP mix (anomaly/eval_ood_traditional.py:434-435,447-448), so that the raw EDS map is read
+// once for normalisation, mix and ranking key.
+struct KeygenFuse {
+  const float* msp;   // raw max-softmax [n_seg*seg_len] (uses minmax slot 1)
+  float* msp_norm;
+  float* mix;
+  float lambda, thr;
+};
+
+template <typename GT, int VEC>
 __global__ void __launch_bounds__(256) keygen_kernel(const float* __restrict__ values, const float* __restrict__ minmax,
                                                      int slot, float* conf_out, const GT* __restrict__ gt,
                                                      uint64_t out_mask, const uint8_t* __restrict__ pos_u8, int kind,
                                                      long long seg_len, uint32_t key_base, uint32_t* __restrict__ keys,
-                                                     unsigned long long* seg_stats) {
+                                                     unsigned long long* seg_stats, const KeygenFuse fz) {
   const int seg = blockIdx.y;
   const size_t base = (size_t)seg * (size_t)seg_len;
-  float lo = 0.f, den = 1.f;
+  float lo = 0.f, den = 1.f, mlo = 0.f, mden = 1.f;
   const bool norm = minmax != nullptr;
   if (norm) {
     lo = minmax[seg * 4 + slot * 2];
     den = __fsub_rn(minmax[seg * 4 + slot * 2 + 1], lo);
+    mlo = minmax[seg * 4 + 2];
+    mden = __fsub_rn(minmax[seg * 4 + 3], mlo);
   }
+  const bool fuse = fz.msp != nullptr;
   unsigned n_pos = 0, n_nan = 0, n_oow = 0;
-  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < seg_len; p += (long long)gridDim.x * blockDim.x) {
-    const size_t i = base + (size_t)p;
-    float v = values[i];
-    if (norm) v = __fdiv_rn(__fsub_rn(v, lo), den);  // NumPy: (x - min) / (max - min), fp32
-    if (conf_out) conf_out[i] = v;
-    const bool pos = is_positive(gt, pos_u8, out_mask, i);
-    n_pos += pos;
-    keys[i] = pack_key(v, kind, pos, key_base, n_nan, n_oow);
+  const long long nvec = seg_len / VEC;
+  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < nvec; q += (long long)gridDim.x * blockDim.x) {
+    const size_t i = base + (size_t)q * VEC;
+    float v[VEC];
+    bool pos[VEC];
+    if constexpr (VEC == 4) {
+      const float4 t = *reinterpret_cast<const float4*>(values + i);
+      v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+      if (pos_u8 || sizeof(GT) == 1) {
+        const uchar4 g = *reinterpret_cast<const uchar4*>((pos_u8 ? pos_u8 : reinterpret_cast<const uint8_t*>(gt)) + i);
+        const unsigned char gg[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) pos[j] = pos_u8 ? (gg[j] != 0) : (gg[j] < 64 && ((out_mask >> gg[j]) & 1ull));
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) pos[j] = is_positive(gt, pos_u8, out_mask, i + j);
+      }
+    } else {
+      v[0] = values[i];
+      pos[0] = is_positive(gt, pos_u8, out_mask, i);
+    }
+    uint32_t key[VEC];
+    float mn[VEC], mx[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      if (norm) v[j] = __fdiv_rn(__fsub_rn(v[j], lo), den);  // NumPy: (x - min) / (max - min), fp32
+      n_pos += pos[j];
+      key[j] = pack_key(v[j], kind, pos[j], key_base, n_nan, n_oow);
+    }
+    if (fuse) {
+      float m[VEC];
+      if constexpr (VEC == 4) {
+        const float4 t = *reinterpret_cast<const float4*>(fz.msp + i);
+        m[0] = t.x; m[1] = t.y; m[2] = t.z; m[3] = t.w;
+      } else {
+        m[0] = fz.msp[i];
+      }
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) {
+        mn[j] = __fdiv_rn(__fsub_rn(m[j], mlo), mden);
+        // NumPy: c = 1 / (1 + exp(lamda * (e - thre))); mix = c*e + (1-c)*mmsp   (float32)
+        const float c = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(__fmul_rn(fz.lambda, __fsub_rn(v[j], fz.thr)))));
+        mx[j] = __fadd_rn(__fmul_rn(c, v[j]), __fmul_rn(__fsub_rn(1.0f, c), mn[j]));
+      }
+    }
+    if constexpr (VEC == 4) {
+      *reinterpret_cast<uint4*>(keys + i) = make_uint4(key[0], key[1], key[2], key[3]);
+      if (conf_out) *reinterpret_cast<float4*>(conf_out + i) = make_float4(v[0], v[1], v[2], v[3]);
+      if (fuse && fz.msp_norm) *reinterpret_cast<float4*>(fz.msp_norm + i) = make_float4(mn[0], mn[1], mn[2], mn[3]);
+      if (fuse && fz.mix) *reinterpret_cast<float4*>(fz.mix + i) = make_float4(mx[0], mx[1], mx[2], mx[3]);
+    } else {
+      keys[i] = key[0];
+      if (conf_out) conf_out[i] = v[0];
+      if (fuse && fz.msp_norm) fz.msp_norm[i] = mn[0];
+      if (fuse && fz.mix) fz.mix[i] = mx[0];
+    }
   }
   // block reduce the three counters
   __shared__ unsigned s_c[3][8];
   unsigned c[3] = {n_pos, n_nan, n_oow};
 #pragma unroll
   for (int j = 0; j < 3; ++j) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) c[j] += __shfl_xor_sync(0xffffffffu, c[j], o);
+    c[j] = __reduce_add_sync(0xffffffffu, c[j]);
     if ((threadIdx.x & 31) == 0) s_c[j][threadIdx.x >> 5] = c[j];
   }
   __syncthreads();
@@ -554,27 +614,38 @@ int dml_ood_keystats(const float* values, int32_t score_kind, int32_t n_seg, int
 int dml_ood_keygen(const float* values, const float* minmax, int32_t minmax_slot, float* conf_out, const uint8_t* gt_u8,
                    const int64_t* gt_i64, uint64_t out_label_mask, const uint8_t* pos_u8, int32_t score_kind,
                    uint32_t key_base, int32_t n_seg, int64_t seg_len, uint32_t* keys, long long* seg_stats,
-                   dml_stream_t stream_) {
+                   const float* msp, float* msp_norm_out, float* mix_out, float lambda, float thr, dml_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (!values || !keys || !seg_stats || n_seg < 0 || seg_len < 0 || n_seg > 65535) return DML_ERR_INVALID_ARG;
   const int nsrc = (gt_u8 != nullptr) + (gt_i64 != nullptr) + (pos_u8 != nullptr);
   if (nsrc != 1) return DML_ERR_INVALID_ARG;
   if (minmax && (minmax_slot < 0 || minmax_slot > 1)) return DML_ERR_INVALID_ARG;
   if (score_kind != 0 && score_kind != 1) return DML_ERR_INVALID_ARG;
+  if ((msp_norm_out || mix_out) && (!msp || !minmax || minmax_slot != 0)) return DML_ERR_INVALID_ARG;
   if (n_seg == 0) return DML_OK;
   DML_CUDA_TRY(cudaMemsetAsync(seg_stats, 0, (size_t)n_seg * 4 * sizeof(long long), stream));
   if (seg_len == 0) return DML_OK;
-  long long bx = (seg_len + 256 * 8 - 1) / (256 * 8);
+  KeygenFuse fz;
+  fz.msp = (msp_norm_out || mix_out) ? msp : nullptr;
+  fz.msp_norm = msp_norm_out; fz.mix = mix_out; fz.lambda = lambda; fz.thr = thr;
+  auto al = [](const void* q, size_t a) { return q == nullptr || (reinterpret_cast<uintptr_t>(q) % a) == 0; };
+  const bool vec4 = (seg_len % 4 == 0) && al(values, 16) && al(keys, 16) && al(conf_out, 16) && al(fz.msp, 16) &&
+                    al(msp_norm_out, 16) && al(mix_out, 16) && al(gt_u8, 4) && al(pos_u8, 4);
+  const long long per_thread = vec4 ? 4 : 1;
+  long long bx = (seg_len / per_thread + 256 * 2 - 1) / (256 * 2);
   const long long cap = n_seg >= 148 * 8 ? 16 : (148 * 32) / n_seg + 1;
   if (bx > cap) bx = cap;
+  if (bx < 1) bx = 1;
   dim3 grid((unsigned)bx, (unsigned)n_seg);
   unsigned long long* st = (unsigned long long*)seg_stats;
-  if (gt_i64)
-    keygen_kernel<long long><<<grid, 256, 0, stream>>>(values, minmax, minmax_slot, conf_out, (const long long*)gt_i64,
-                                                       out_label_mask, nullptr, score_kind, seg_len, key_base, keys, st);
-  else
-    keygen_kernel<uint8_t><<<grid, 256, 0, stream>>>(values, minmax, minmax_slot, conf_out, gt_u8, out_label_mask, pos_u8,
-                                                     score_kind, seg_len, key_base, keys, st);
+  const long long* g64 = (const long long*)gt_i64;
+  if (gt_i64) {
+    if (vec4) keygen_kernel<long long, 4><<<grid, 256, 0, stream>>>(values, minmax, minmax_slot, conf_out, g64, out_label_mask, nullptr, score_kind, seg_len, key_base, keys, st, fz);
+    else keygen_kernel<long long, 1><<<grid, 256, 0, stream>>>(values, minmax, minmax_slot, conf_out, g64, out_label_mask, nullptr, score_kind, seg_len, key_base, keys, st, fz);
+  } else {
+    if (vec4) keygen_kernel<uint8_t, 4><<<grid, 256, 0, stream>>>(values, minmax, minmax_slot, conf_out, gt_u8, out_label_mask, pos_u8, score_kind, seg_len, key_base, keys, st, fz);
+    else keygen_kernel<uint8_t, 1><<<grid, 256, 0, stream>>>(values, minmax, minmax_slot, conf_out, gt_u8, out_label_mask, pos_u8, score_kind, seg_len, key_base, keys, st, fz);
+  }
   DML_LAUNCH_CHECK();
   return DML_OK;
 }

@@ -11,6 +11,19 @@ __device__ __forceinline__ unsigned lanemask_lt() {
   return m;
 }
 
+// Peer mask of the lanes holding the same 8-bit digit, built from 8 warp ballots (full-rate
+// VOTE + LOP3) instead of MATCH.ANY, which is far slower on sm_100.  Invalid lanes get an empty mask.
+__device__ __forceinline__ unsigned match_digit8(uint32_t d, bool valid) {
+  unsigned peers = __ballot_sync(0xffffffffu, valid);
+#pragma unroll
+  for (int b = 0; b < RADIX_BITS; ++b) {
+    const bool bit = (d >> b) & 1u;
+    const unsigned vote = __ballot_sync(0xffffffffu, bit);
+    peers &= bit ? vote : ~vote;
+  }
+  return valid ? peers : 0u;
+}
+
 // ---- digit histograms of every pass in one read of the keys --------------------------------
 // Warp-private shared histograms updated by the match-group leader with plain LDS/STS (no atomics).
 constexpr int HIST_TILES_PER_BLOCK = 16;
@@ -47,10 +60,17 @@ __global__ void __launch_bounds__(SORT_THREADS) hist_kernel(const uint32_t* __re
 #pragma unroll
       for (int p = 0; p < MAX_PASSES; ++p) {
         if (p < n_passes) {
-          const uint32_t d = valid ? ((key[u] >> shifts[p]) & (RADIX - 1)) : 0xffffffffu;
-          const unsigned peers = __match_any_sync(0xffffffffu, d);
-          if (valid && lane == (__ffs(peers) - 1)) s_h[w][p][d] += (uint32_t)__popc(peers);
-          __syncwarp();
+          const uint32_t d = (key[u] >> shifts[p]) & (RADIX - 1);
+          if (p < n_passes - 2) {
+            // low digit places are close to uniform: a warp-private shared atomic sees few same-address lanes
+            if (valid) atomicAdd(&s_h[w][p][d], 1u);
+          } else {
+            // the top places of float keys are heavily skewed (a warp usually holds 1-3 distinct values):
+            // group equal digits with ballots, the group leader adds the group size (plain LDS/STS)
+            const unsigned peers = match_digit8(d, valid);
+            if (valid && lane == (__ffs(peers) - 1)) s_h[w][p][d] += (uint32_t)__popc(peers);
+            __syncwarp();
+          }
         }
       }
     }
@@ -131,22 +151,27 @@ __global__ void __launch_bounds__(SORT_THREADS) onesweep_kernel(const uint32_t* 
     key[i] = idx < nvalid ? src[idx] : 0xffffffffu;
   }
   // ---- rank within warp ----------------------------------------------------------------------
+  // phase 1 (pure ALU, full ILP across items): peer masks; phase 2: the group leader advances the
+  // warp-private running count of its digit and broadcasts the group's base rank.
   const unsigned lt = lanemask_lt();
+  unsigned peers[SORT_ITEMS];
 #pragma unroll
   for (int i = 0; i < SORT_ITEMS; ++i) {
     const int idx = wbase + i * 32 + lane;
-    const bool valid = idx < nvalid;
-    const uint32_t d = valid ? ((key[i] >> shift) & (RADIX - 1)) : 0xffffffffu;
-    const unsigned peers = __match_any_sync(0xffffffffu, d);
-    const int leader = __ffs(peers) - 1;
+    peers[i] = match_digit8((key[i] >> shift) & (RADIX - 1), idx < nvalid);
+  }
+#pragma unroll
+  for (int i = 0; i < SORT_ITEMS; ++i) {
+    const uint32_t d = (key[i] >> shift) & (RADIX - 1);
+    const int leader = __ffs(peers[i]) - 1;  // -1 for invalid lanes
     uint32_t c = 0;
-    if (valid && lane == leader) {
+    if (lane == leader) {
       c = s_whist[w][d];
-      s_whist[w][d] = c + (uint32_t)__popc(peers);
+      s_whist[w][d] = c + (uint32_t)__popc(peers[i]);
     }
     __syncwarp();
-    c = __shfl_sync(0xffffffffu, c, leader);
-    rank[i] = c + (uint32_t)__popc(peers & lt);
+    c = __shfl_sync(0xffffffffu, c, leader < 0 ? 0 : leader);
+    rank[i] = c + (uint32_t)__popc(peers[i] & lt);
   }
   __syncthreads();
 

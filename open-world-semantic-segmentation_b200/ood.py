@@ -57,7 +57,9 @@ def eval_segments(values: torch.Tensor, n_seg: int, seg_len: int, *, gt: Optiona
                   out_labels: Sequence[int] = (13,), positive: Optional[torch.Tensor] = None, score_kind: int = 0,
                   key_base: int = KEY_BASE_NONNEG, minmax: Optional[torch.Tensor] = None, minmax_slot: int = 0,
                   conf_out: Optional[torch.Tensor] = None, recall_level: float = RECALL_LEVEL_DEFAULT,
-                  workspace: Optional[OodWorkspace] = None):
+                  workspace: Optional[OodWorkspace] = None, msp: Optional[torch.Tensor] = None,
+                  msp_norm_out: Optional[torch.Tensor] = None, mix_out: Optional[torch.Tensor] = None,
+                  lam: float = 50.0, thr: float = 0.2):
     """Evaluate ``n_seg`` independent segments of ``seg_len`` (score, label) pairs each.
 
     values: flat fp32 CUDA tensor (n_seg*seg_len): a ``conf`` map ranked as score = -conf
@@ -66,6 +68,8 @@ def eval_segments(values: torch.Tensor, n_seg: int, seg_len: int, *, gt: Optiona
             (uint8, non-zero = positive) directly.
     minmax: optional [n_seg,4] per-segment (min,max) pairs; the kernel then ranks the min-max
             normalised value (slot 0: eds, 1: msp) and can store it to ``conf_out``.
+    msp / msp_norm_out / mix_out: fused score maps (slot 0 only): MMSP = normalised ``msp`` and the
+            EDS/MMSP mix (anomaly/eval_ood_traditional.py:434-435,447-448) written in the same pass.
     Returns (results, stats): device tensors -- results float64 [n_seg,7] viewed as
     (auroc, aupr, fpr, n_pos, n_neg, n_nan, n_groups; the last four are int64 bit patterns),
     stats int64 [n_seg,4] = (n_pos, n_nan, n_out_of_window, 0).  No host synchronisation.
@@ -106,7 +110,8 @@ def eval_segments(values: torch.Tensor, n_seg: int, seg_len: int, *, gt: Optiona
         s = stream_ptr(dev)
         check(lib().dml_ood_keygen(ptr(values), ptr(minmax), minmax_slot, ptr(conf_out), ptr(gt_u8), ptr(gt_i64),
                                    label_mask(out_labels) if positive is None else 0, ptr(pos_u8), score_kind, key_base,
-                                   n_seg, seg_len, ptr(keys), ptr(stats), s), "dml_ood_keygen")
+                                   n_seg, seg_len, ptr(keys), ptr(stats), ptr(msp), ptr(msp_norm_out), ptr(mix_out),
+                                   lam, thr, s), "dml_ood_keygen")
         check(lib().dml_ood_eval_segments(ptr(keys), ptr(stats), n_seg, seg_len, recall_level, ptr(scratch),
                                           scratch.numel(), ptr(results), s), "dml_ood_eval_segments")
     return results, stats
@@ -196,7 +201,7 @@ def measures_from_scores(scores: torch.Tensor, positive: torch.Tensor, recall_le
             keys = ws.get("keys", 4 * m)
             stats = ws.get("stats", 32).view(torch.int64)[:4].view(1, 4)
             check(lib().dml_ood_keygen(ptr(sc), None, 0, None, None, None, 0, ptr(po), 1, base, 1, m, ptr(keys),
-                                       ptr(stats), stream_ptr(dev)), "dml_ood_keygen")
+                                       ptr(stats), None, None, None, 0.0, 0.0, stream_ptr(dev)), "dml_ood_keygen")
             nbytes = lib().dml_ood_workspace_bytes(1, m)
             scratch = ws.get("scratch", nbytes)
             sorted_ptr = C.c_void_p()

@@ -88,14 +88,21 @@ def test_fused_normalisation_keygen():
     gt = rng.integers(0, 14, (3, 5000)).astype(np.uint8)
     mm = np.zeros((3, 4), np.float32)
     mm[:, 0], mm[:, 1] = raw.min(1), raw.max(1)
+    msp = (0.2 + 0.8 * rng.random((3, 5000))).astype(np.float32)
+    mm[:, 2], mm[:, 3] = msp.min(1), msp.max(1)
     conf_out = torch.empty(3, 5000, device="cuda")
+    mmsp_out, mix_out = torch.empty(3, 5000, device="cuda"), torch.empty(3, 5000, device="cuda")
     res, stats = ood.eval_segments(torch.from_numpy(raw).cuda(), 3, 5000, gt=torch.from_numpy(gt).cuda(), out_labels=(13,),
-                                   minmax=torch.from_numpy(mm).cuda(), minmax_slot=0, conf_out=conf_out)
+                                   minmax=torch.from_numpy(mm).cuda(), minmax_slot=0, conf_out=conf_out,
+                                   msp=torch.from_numpy(msp).cuda(), msp_norm_out=mmsp_out, mix_out=mix_out)
     vals, _ = ood.results_to_host(res, stats)
     for s in range(3):
         conf = O.normalization(raw[s])
         np.testing.assert_array_equal(conf_out[s].cpu().numpy(), conf)
         np.testing.assert_allclose(vals[s], O.eval_ood_measure(conf, gt[s].astype(np.int64), (13,)), atol=1e-12)
+        mmsp = O.normalization(msp[s])
+        np.testing.assert_array_equal(mmsp_out[s].cpu().numpy(), mmsp)
+        np.testing.assert_allclose(mix_out[s].cpu().numpy(), O.score_mix(conf, mmsp), rtol=1e-5, atol=1e-6)
 
 
 def test_large_single_segment_properties():
