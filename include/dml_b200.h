@@ -146,13 +146,15 @@ DML_API int dml_plm_merge(uint8_t* base_u8, int64_t* base_i64, const uint8_t* he
  * Forward writes 4 doubles: loss, CE, VL, Inter and the valid-pixel count as double in [4].
  * `partials` is a workspace of dml_loss_workspace_bytes(B,H,W).
  * Backward recomputes the distances and writes dL/dx [B,D,H,W] scaled by *grad_out (device scalar).
+ * x_is_logits != 0: `x` already holds the logits z [B,K,H,W] (the reference criterion's signature,
+ * utils/loss.py:34 `forward(logit, target, features_in)`); mu must be NULL and dx is dL/dz.
  * ------------------------------------------------------------------------------------ */
 DML_API size_t dml_loss_workspace_bytes(int32_t B, int32_t H, int32_t W);
-DML_API int dml_loss_forward(const float* x, const float* mu, float diag_m, const uint8_t* target_u8,
+DML_API int dml_loss_forward(const float* x, int32_t x_is_logits, const float* mu, float diag_m, const uint8_t* target_u8,
                      const int64_t* target_i64, int64_t ignore_index, int32_t B, int32_t D, int32_t K,
                      int32_t H, int32_t W, double alpha, double beta, void* partials,
                      double* out5, dml_stream_t stream);
-DML_API int dml_loss_backward(const float* x, const float* mu, float diag_m, const uint8_t* target_u8,
+DML_API int dml_loss_backward(const float* x, int32_t x_is_logits, const float* mu, float diag_m, const uint8_t* target_u8,
                       const int64_t* target_i64, int64_t ignore_index, int32_t B, int32_t D, int32_t K,
                       int32_t H, int32_t W, double alpha, double beta, const double* out5,
                       const float* grad_out, float* dx, dml_stream_t stream);

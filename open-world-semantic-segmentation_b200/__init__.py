@@ -13,7 +13,7 @@ There is no CPU / PyTorch fallback: every entry point raises if the CUDA library
 from . import _lib  # noqa: F401
 from ._lib import DmlError, load_library  # noqa: F401
 from . import head, ood  # noqa: F401
-from . import autograd, anomaly  # noqa: F401
+from . import autograd, anomaly, deeplab, prototypes  # noqa: F401
 from .autograd import distance_logits, dml_loss  # noqa: F401
 from .head import HeadOutput, confusion_counts, dml_head, finalize_scores, plm_merge  # noqa: F401
 

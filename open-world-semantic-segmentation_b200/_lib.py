@@ -61,10 +61,10 @@ SIGNATURES = {
                                 C.c_void_p, C.c_void_p]),
     "dml_plm_merge": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]),
     "dml_loss_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32]),
-    "dml_loss_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
+    "dml_loss_forward": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
                                    C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_void_p,
                                    C.c_void_p, C.c_void_p]),
-    "dml_loss_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
+    "dml_loss_backward": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
                                     C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_void_p,
                                     C.c_void_p, C.c_void_p, C.c_void_p]),
     "dml_class_sums_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32, C.c_int64]),

@@ -50,7 +50,7 @@ class _DmlLoss(torch.autograd.Function):
     """Fused DCE + alpha*VL + beta*Inter straight from the embedding (kernel (b))."""
 
     @staticmethod
-    def forward(ctx, x, target, centers, magnitude, alpha, beta, ignore_index):
+    def forward(ctx, x, target, centers, magnitude, alpha, beta, ignore_index, is_logits):
         require_cuda(x, "x")
         x = x.contiguous()
         target = target.contiguous()
@@ -65,11 +65,12 @@ class _DmlLoss(torch.autograd.Function):
         partials = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         u8 = target.dtype == torch.uint8
         with torch.cuda.device(dev):
-            check(lib().dml_loss_forward(ptr(x), ptr(mu), magnitude, ptr(target) if u8 else None,
+            check(lib().dml_loss_forward(ptr(x), 1 if is_logits else 0, ptr(mu), magnitude, ptr(target) if u8 else None,
                                          None if u8 else ptr(target), ignore_index, B, D, K, Hh, Ww, alpha, beta,
                                          ptr(partials), ptr(out5), stream_ptr(dev)), "dml_loss_forward")
         ctx.save_for_backward(x, target, out5)
         ctx.mu, ctx.magnitude, ctx.alpha, ctx.beta, ctx.ignore_index, ctx.K = mu, magnitude, alpha, beta, ignore_index, K
+        ctx.is_logits = is_logits
         ctx.mark_non_differentiable(out5)
         return out5[0].to(torch.float32), out5
 
@@ -82,20 +83,22 @@ class _DmlLoss(torch.autograd.Function):
         g = grad_loss.to(device=dev, dtype=torch.float32).contiguous().view(1)
         u8 = target.dtype == torch.uint8
         with torch.cuda.device(dev):
-            check(lib().dml_loss_backward(ptr(x), ptr(ctx.mu), ctx.magnitude, ptr(target) if u8 else None,
+            check(lib().dml_loss_backward(ptr(x), 1 if ctx.is_logits else 0, ptr(ctx.mu), ctx.magnitude, ptr(target) if u8 else None,
                                           None if u8 else ptr(target), ctx.ignore_index, B, D, ctx.K, Hh, Ww, ctx.alpha,
                                           ctx.beta, ptr(out5), ptr(g), ptr(dx), stream_ptr(dev)), "dml_loss_backward")
-        return dx, None, None, None, None, None, None
+        return dx, None, None, None, None, None, None, None
 
 
 def dml_loss(x: torch.Tensor, target: torch.Tensor, *, centers: Optional[torch.Tensor] = None,
              magnitude: float = H.DEFAULT_MAGNITUDE, alpha: float = 0.0, beta: float = 0.0, ignore_index: int = 255,
-             return_parts: bool = False):
+             return_parts: bool = False, input_is_logits: bool = False):
     """loss = (CE + alpha*VL + beta*Inter)/n from the embedding ``x`` [B,D,H,W] and labels [B,H,W].
-    ``return_parts`` also returns the float64 device vector (loss, CE, VL, Inter, n_valid)."""
+    ``return_parts`` also returns the float64 device vector (loss, CE, VL, Inter, n_valid).
+    ``input_is_logits``: ``x`` holds the logits z [B,K,H,W] (the reference criterion's calling convention)."""
     if centers is not None:
         m = H.scaled_identity_magnitude(centers)
         if m is not None and centers.shape[0] == x.shape[1]:
             centers, magnitude = None, m
-    loss, parts = _DmlLoss.apply(x, target, centers, float(magnitude), float(alpha), float(beta), int(ignore_index))
+    loss, parts = _DmlLoss.apply(x, target, centers, float(magnitude), float(alpha), float(beta), int(ignore_index),
+                                 bool(input_is_logits))
     return (loss, parts) if return_parts else loss

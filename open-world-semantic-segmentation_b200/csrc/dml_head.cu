@@ -75,7 +75,9 @@ __global__ void __launch_bounds__(256) plm_merge_kernel(T* base, const T* __rest
 
 static int pick_vec(const dml_head_params* p, long long hw) {
   auto al = [](const void* q, size_t a) { return q == nullptr || (reinterpret_cast<uintptr_t>(q) % a) == 0; };
-  int vmax = 4;
+  // measured on B200 (profiles/): 2 pixels/thread (48-56 registers, 4 resident CTAs/SM) beats 4 for
+  // D > 8 because load and compute phases of more co-resident CTAs overlap; small D keeps 4.
+  int vmax = p->D > 8 ? 2 : 4;
   if (const char* e = getenv("DML_HEAD_VEC")) {  // tuning knob: cap the pixels per thread
     const int v = atoi(e);
     if (v == 1 || v == 2 || v == 4) vmax = v;

@@ -21,7 +21,7 @@ int head_dispatch_1_8(int D, int mode, int vec, bool extra, const HeadArgs& a, c
   }
 }
 
-int loss_dispatch_1_8(int D, bool ident, int vec, bool bwd, const LossArgs& a, int gx, cudaStream_t s) {
+int loss_dispatch_1_8(int D, int mode, int vec, bool bwd, const LossArgs& a, int gx, cudaStream_t s) {
   switch (D) {
     DML_LOSS_CASE(1)
     DML_LOSS_CASE(2)

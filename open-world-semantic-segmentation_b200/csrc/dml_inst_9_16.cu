@@ -21,7 +21,7 @@ int head_dispatch_9_16(int D, int mode, int vec, bool extra, const HeadArgs& a, 
   }
 }
 
-int loss_dispatch_9_16(int D, bool ident, int vec, bool bwd, const LossArgs& a, int gx, cudaStream_t s) {
+int loss_dispatch_9_16(int D, int mode, int vec, bool bwd, const LossArgs& a, int gx, cudaStream_t s) {
   switch (D) {
     DML_LOSS_CASE(9)
     DML_LOSS_CASE(10)

@@ -66,13 +66,15 @@ __global__ void __launch_bounds__(256) class_sums_finalize_kernel(const double* 
   else counts[(size_t)b * n_cls + c] = (long long)(t + 0.5);
 }
 
-int loss_common(bool bwd, const float* x, const float* mu, float diag_m, const uint8_t* t_u8, const int64_t* t_i64,
+int loss_common(bool bwd, bool is_logits, const float* x, const float* mu, float diag_m, const uint8_t* t_u8, const int64_t* t_i64,
                 int64_t ignore_index, int B, int D, int K, int H, int W, double alpha, double beta, void* partials,
                 double* out5, const float* grad_out, float* dx, cudaStream_t stream) {
   if (!x || (!t_u8 == !t_i64) || B < 1 || D < 1 || K < 1 || H < 1 || W < 1 || !out5) return DML_ERR_INVALID_ARG;
   if (D > DML_MAX_DIM || K > DML_MAX_DIM) return DML_ERR_UNSUPPORTED_DIM;
   if (B > 65535) return DML_ERR_INVALID_ARG;
-  const bool ident = mu == nullptr;
+  if (is_logits && mu) return DML_ERR_INVALID_ARG;
+  const int mode = is_logits ? LOSS_LOGITS : (mu == nullptr ? LOSS_IDENT : LOSS_DENSE);
+  const bool ident = mode != LOSS_DENSE;  // vectorised, K == D paths
   if (ident && K != D) return DML_ERR_INVALID_ARG;
   if (bwd ? (!grad_out || !dx) : !partials) return DML_ERR_INVALID_ARG;
   const long long hw = (long long)H * W;
@@ -85,10 +87,10 @@ int loss_common(bool bwd, const float* x, const float* mu, float diag_m, const u
   a.partials = reinterpret_cast<double*>(partials); a.out5 = out5; a.grad_out = grad_out; a.dx = dx;
   const int gx = loss_grid_x(hw, vec);
   int rc;
-  if (D <= 8) rc = loss_dispatch_1_8(D, ident, vec, bwd, a, gx, stream);
-  else if (D <= 16) rc = loss_dispatch_9_16(D, ident, vec, bwd, a, gx, stream);
-  else if (D <= 24) rc = loss_dispatch_17_24(D, ident, vec, bwd, a, gx, stream);
-  else rc = loss_dispatch_25_32(D, ident, vec, bwd, a, gx, stream);
+  if (D <= 8) rc = loss_dispatch_1_8(D, mode, vec, bwd, a, gx, stream);
+  else if (D <= 16) rc = loss_dispatch_9_16(D, mode, vec, bwd, a, gx, stream);
+  else if (D <= 24) rc = loss_dispatch_17_24(D, mode, vec, bwd, a, gx, stream);
+  else rc = loss_dispatch_25_32(D, mode, vec, bwd, a, gx, stream);
   if (rc != DML_OK || bwd) return rc;
   loss_finalize_kernel<<<1, 256, 0, stream>>>(a.partials, gx * B, B, hw, alpha, beta, out5);
   DML_LAUNCH_CHECK();
@@ -109,17 +111,17 @@ size_t dml_loss_workspace_bytes(int32_t B, int32_t H, int32_t W) {
   return (size_t)B * loss_grid_x((long long)H * W, 1) * 4 * sizeof(double);
 }
 
-int dml_loss_forward(const float* x, const float* mu, float diag_m, const uint8_t* target_u8, const int64_t* target_i64,
-                     int64_t ignore_index, int32_t B, int32_t D, int32_t K, int32_t H, int32_t W, double alpha, double beta,
-                     void* partials, double* out5, dml_stream_t stream) {
-  return loss_common(false, x, mu, diag_m, target_u8, target_i64, ignore_index, B, D, K, H, W, alpha, beta, partials, out5,
+int dml_loss_forward(const float* x, int32_t x_is_logits, const float* mu, float diag_m, const uint8_t* target_u8,
+                     const int64_t* target_i64, int64_t ignore_index, int32_t B, int32_t D, int32_t K, int32_t H, int32_t W,
+                     double alpha, double beta, void* partials, double* out5, dml_stream_t stream) {
+  return loss_common(false, x_is_logits != 0, x, mu, diag_m, target_u8, target_i64, ignore_index, B, D, K, H, W, alpha, beta, partials, out5,
                      nullptr, nullptr, (cudaStream_t)stream);
 }
 
-int dml_loss_backward(const float* x, const float* mu, float diag_m, const uint8_t* target_u8, const int64_t* target_i64,
-                      int64_t ignore_index, int32_t B, int32_t D, int32_t K, int32_t H, int32_t W, double alpha, double beta,
-                      const double* out5, const float* grad_out, float* dx, dml_stream_t stream) {
-  return loss_common(true, x, mu, diag_m, target_u8, target_i64, ignore_index, B, D, K, H, W, alpha, beta, nullptr,
+int dml_loss_backward(const float* x, int32_t x_is_logits, const float* mu, float diag_m, const uint8_t* target_u8,
+                      const int64_t* target_i64, int64_t ignore_index, int32_t B, int32_t D, int32_t K, int32_t H, int32_t W,
+                      double alpha, double beta, const double* out5, const float* grad_out, float* dx, dml_stream_t stream) {
+  return loss_common(true, x_is_logits != 0, x, mu, diag_m, target_u8, target_i64, ignore_index, B, D, K, H, W, alpha, beta, nullptr,
                      const_cast<double*>(out5), grad_out, dx, (cudaStream_t)stream);
 }
 

@@ -38,12 +38,19 @@ struct LossArgs {
   float* dx;
 };
 
-template <int D, bool IDENT, int VEC, bool BWD>
+// MODE: LOSS_DENSE (prototype table), LOSS_IDENT (mu = m I), LOSS_LOGITS (x already holds the logits z:
+// the reference's criterion signature, utils/loss.py:34 -- the gradient is then dL/dz itself).
+constexpr int LOSS_DENSE = 0, LOSS_IDENT = 1, LOSS_LOGITS = 2;
+
+template <int D, int MODE, int VEC, bool BWD>
 __global__ void __launch_bounds__(LOSS_THREADS) loss_kernel(const LossArgs a) {
+  constexpr bool IDENT = (MODE == LOSS_IDENT);
+  constexpr bool LOGITS = (MODE == LOSS_LOGITS);
+  constexpr bool DENSE = (MODE == LOSS_DENSE);
   extern __shared__ __align__(16) unsigned char smem_dyn[];
   float* s_mu = reinterpret_cast<float*>(smem_dyn);  // dense only: [K][D]
-  const int K = IDENT ? D : a.K;
-  if constexpr (!IDENT) {
+  const int K = DENSE ? a.K : D;
+  if constexpr (DENSE) {
     for (int i = threadIdx.x; i < K * D; i += LOSS_THREADS) s_mu[i] = a.mu[i];
     __syncthreads();
   }
@@ -83,7 +90,7 @@ __global__ void __launch_bounds__(LOSS_THREADS) loss_kernel(const LossArgs a) {
 
       // u_k = z_k - z_ext (<= 0), with z_ext the largest logit.  mu = m I: u_k = 2m (x_k - x_ext) from the
       // exact difference of embeddings (x_ext = max x for m > 0, min x for m < 0); dense: from the distances.
-      float zk[IDENT ? 1 : DML_MAX_DIM];  // dense: logits kept for the second sweep
+      float zk[DENSE ? DML_MAX_DIM : 1];  // dense: logits kept for the second sweep
       float ext = 0.f, dy = 0.f, dsum = 0.f;
       int kext = 0;
       if constexpr (IDENT) {
@@ -92,6 +99,14 @@ __global__ void __launch_bounds__(LOSS_THREADS) loss_kernel(const LossArgs a) {
         for (int k = 1; k < D; ++k) {
           const bool better = two_m >= 0.f ? (x[k][v] > ext) : (x[k][v] < ext);
           if (better) { ext = x[k][v]; kext = k; }
+        }
+      } else if constexpr (LOGITS) {
+        ext = x[0][v];
+        dsum = -x[0][v];
+#pragma unroll
+        for (int k = 1; k < D; ++k) {
+          if (x[k][v] > ext) { ext = x[k][v]; kext = k; }
+          dsum -= x[k][v];
         }
       } else {
         ext = __int_as_float(0xff800000);
@@ -114,11 +129,11 @@ __global__ void __launch_bounds__(LOSS_THREADS) loss_kernel(const LossArgs a) {
       // r = sum_{k != kext} exp(u_k); the extremal term is exactly 1 and is kept out of the sum so that
       // log1p(r) stays accurate for well-separated pixels.  uy = u_y.
       float r = 0.f, uy = 0.f;
-      if constexpr (IDENT) {
+      if constexpr (IDENT || LOGITS) {
 #pragma unroll
         for (int k = 0; k < D; ++k) {
-          const float u = two_m * (x[k][v] - ext);
-          if (k == y) uy = u;
+          const float u = (LOGITS ? 1.0f : two_m) * (x[k][v] - ext);
+          if (k == y) { uy = u; if (LOGITS) dy = -x[k][v]; }
           if (k != kext) r += ex2_approx(u * LOG2E);
         }
       } else {
@@ -156,13 +171,13 @@ __global__ void __launch_bounds__(LOSS_THREADS) loss_kernel(const LossArgs a) {
         // g_k = gscale * [ (p_k - [k=y]) / Nv - a_t [k=y] + b_t [k!=y] ]  (valid pixels only)
         const float inv_s = 1.0f / (1.0f + r);
         const float G = gscale * (-a_t + b_t * (float)(K - 1));  // sum_k g_k (softmax sums to 1)
-        if constexpr (IDENT) {
+        if constexpr (IDENT || LOGITS) {
 #pragma unroll
           for (int d = 0; d < D; ++d) {
-            const float pk = (d == kext ? 1.0f : ex2_approx(two_m * (x[d][v] - ext) * LOG2E)) * inv_s;
+            const float pk = (d == kext ? 1.0f : ex2_approx((LOGITS ? 1.0f : two_m) * (x[d][v] - ext) * LOG2E)) * inv_s;
             const float oh = (d == y) ? 1.f : 0.f;
             const float gk = gscale * ((pk - oh) * inv_nv - a_t * oh + b_t * (1.f - oh));
-            const float g = -2.0f * (G * x[d][v] - a.diag_m * gk);
+            const float g = LOGITS ? gk : -2.0f * (G * x[d][v] - a.diag_m * gk);
             x[d][v] = valid ? g : 0.f;
           }
         } else {
@@ -214,27 +229,28 @@ __global__ void __launch_bounds__(LOSS_THREADS) loss_kernel(const LossArgs a) {
   }
 }
 
-template <int D, bool IDENT, int VEC, bool BWD>
+template <int D, int MODE, int VEC, bool BWD>
 int launch_loss(const LossArgs& a, int grid_x, cudaStream_t stream) {
   dim3 grid((unsigned)grid_x, (unsigned)a.B);
-  const size_t smem = IDENT ? 0 : (size_t)a.K * D * sizeof(float);
-  loss_kernel<D, IDENT, VEC, BWD><<<grid, LOSS_THREADS, smem, stream>>>(a);
+  const size_t smem = MODE == LOSS_DENSE ? (size_t)a.K * D * sizeof(float) : 0;
+  loss_kernel<D, MODE, VEC, BWD><<<grid, LOSS_THREADS, smem, stream>>>(a);
   DML_LAUNCH_CHECK();
   return DML_OK;
 }
 
-#define DML_LOSS_CASE(Dv)                                                                                     \
-  case Dv:                                                                                                    \
-    if (ident) {                                                                                              \
-      if (bwd) return vec == 4 ? launch_loss<Dv, true, 4, true>(a, gx, s) : launch_loss<Dv, true, 1, true>(a, gx, s);   \
-      return vec == 4 ? launch_loss<Dv, true, 4, false>(a, gx, s) : launch_loss<Dv, true, 1, false>(a, gx, s);          \
-    }                                                                                                         \
-    if (bwd) return launch_loss<Dv, false, 1, true>(a, gx, s);                                                \
-    return launch_loss<Dv, false, 1, false>(a, gx, s);
+#define DML_LOSS_CASE_M(Dv, MD)                                                                              \
+  if (bwd) return vec == 4 ? launch_loss<Dv, MD, 4, true>(a, gx, s) : launch_loss<Dv, MD, 1, true>(a, gx, s);     \
+  return vec == 4 ? launch_loss<Dv, MD, 4, false>(a, gx, s) : launch_loss<Dv, MD, 1, false>(a, gx, s);
+#define DML_LOSS_CASE(Dv)                                          \
+  case Dv:                                                         \
+    if (mode == LOSS_IDENT) { DML_LOSS_CASE_M(Dv, LOSS_IDENT) }    \
+    if (mode == LOSS_LOGITS) { DML_LOSS_CASE_M(Dv, LOSS_LOGITS) }  \
+    if (bwd) return launch_loss<Dv, LOSS_DENSE, 1, true>(a, gx, s); \
+    return launch_loss<Dv, LOSS_DENSE, 1, false>(a, gx, s);
 
-int loss_dispatch_1_8(int D, bool ident, int vec, bool bwd, const LossArgs& a, int gx, cudaStream_t s);
-int loss_dispatch_9_16(int D, bool ident, int vec, bool bwd, const LossArgs& a, int gx, cudaStream_t s);
-int loss_dispatch_17_24(int D, bool ident, int vec, bool bwd, const LossArgs& a, int gx, cudaStream_t s);
-int loss_dispatch_25_32(int D, bool ident, int vec, bool bwd, const LossArgs& a, int gx, cudaStream_t s);
+int loss_dispatch_1_8(int D, int mode, int vec, bool bwd, const LossArgs& a, int gx, cudaStream_t s);
+int loss_dispatch_9_16(int D, int mode, int vec, bool bwd, const LossArgs& a, int gx, cudaStream_t s);
+int loss_dispatch_17_24(int D, int mode, int vec, bool bwd, const LossArgs& a, int gx, cudaStream_t s);
+int loss_dispatch_25_32(int D, int mode, int vec, bool bwd, const LossArgs& a, int gx, cudaStream_t s);
 
 }  // namespace dml
