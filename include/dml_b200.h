@@ -229,6 +229,11 @@ DML_API int dml_ood_eval_segments(uint32_t* keys, const long long* seg_stats, in
  * i64 best_idx; i64 best_fps; i64 n_groups } -- ranges combine by (+, +, argmin(dist, -idx), +). */
 DML_API int dml_ood_sort(uint32_t* keys, int32_t n_seg, int64_t seg_len, int32_t begin_bit, int32_t end_bit,
                  void* workspace, size_t workspace_bytes, uint32_t** sorted_out, dml_stream_t stream);
+/* positions[j] = first index with sorted_keys[i] >= queries[j] (cuts a sorted shard at the range splitters);
+ * count = number of keys with the positive bit set.  All pointers device. */
+DML_API int dml_ood_lower_bound(const uint32_t* sorted_keys, int64_t n, const uint32_t* queries, int32_t n_queries,
+                        long long* positions, dml_stream_t stream);
+DML_API int dml_ood_count_positive(const uint32_t* keys, int64_t n, long long* count, dml_stream_t stream);
 DML_API int dml_ood_scan_range(const uint32_t* sorted_keys, int64_t n, const long long* range_info,
                        double recall_level, void* workspace, size_t workspace_bytes, void* partial_out,
                        dml_stream_t stream);

@@ -535,6 +535,28 @@ __global__ void __launch_bounds__(FIN_THREADS) scan_finalize_kernel(const TilePa
   }
 }
 
+// first index i with sorted[i] >= q (one thread per query; used to cut sorted shards at the splitters)
+__global__ void lower_bound_kernel(const uint32_t* __restrict__ sorted, long long n, const uint32_t* __restrict__ queries,
+                                   int nq, long long* __restrict__ pos) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nq) return;
+  const uint32_t q = queries[t];
+  long long lo = 0, hi = n;
+  while (lo < hi) {
+    const long long mid = lo + ((hi - lo) >> 1);
+    if (sorted[mid] < q) lo = mid + 1; else hi = mid;
+  }
+  pos[t] = lo;
+}
+
+// positives (bit 0) in a key range
+__global__ void __launch_bounds__(256) count_pos_kernel(const uint32_t* __restrict__ keys, long long n, unsigned long long* out) {
+  unsigned c = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) c += keys[i] & 1u;
+  c = __reduce_add_sync(0xffffffffu, c);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, (unsigned long long)c);
+}
+
 // RangeInfo of whole segments: everything starts at zero, totals from the key-gen statistics
 __global__ void range_info_from_stats_kernel(const unsigned long long* __restrict__ seg_stats, long long seg_len, int n_seg,
                                              RangeInfo* __restrict__ info) {
@@ -683,6 +705,28 @@ int dml_ood_sort(uint32_t* keys, int32_t n_seg, int64_t seg_len, int32_t begin_b
   const SortPlan plan = make_sort_plan(n_seg, seg_len, begin_bit, end_bit);
   if (workspace_bytes < plan.off_end) return DML_ERR_WORKSPACE;
   return radix_sort_segments(keys, plan, workspace, sorted_out, stream);
+}
+
+int dml_ood_lower_bound(const uint32_t* sorted_keys, int64_t n, const uint32_t* queries, int32_t n_queries,
+                        long long* positions, dml_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (n < 0 || n_queries < 0 || (n > 0 && !sorted_keys) || (n_queries > 0 && (!queries || !positions))) return DML_ERR_INVALID_ARG;
+  if (n_queries == 0) return DML_OK;
+  lower_bound_kernel<<<ceil_div_i(n_queries, 128), 128, 0, stream>>>(sorted_keys, n, queries, n_queries, positions);
+  DML_LAUNCH_CHECK();
+  return DML_OK;
+}
+
+int dml_ood_count_positive(const uint32_t* keys, int64_t n, long long* count, dml_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (n < 0 || !count || (n > 0 && !keys)) return DML_ERR_INVALID_ARG;
+  DML_CUDA_TRY(cudaMemsetAsync(count, 0, sizeof(long long), stream));
+  if (n == 0) return DML_OK;
+  long long blocks = (n + 256 * 16 - 1) / (256 * 16);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  count_pos_kernel<<<(int)blocks, 256, 0, stream>>>(keys, n, (unsigned long long*)count);
+  DML_LAUNCH_CHECK();
+  return DML_OK;
 }
 
 int dml_ood_scan_range(const uint32_t* sorted_keys, int64_t n, const long long* range_info, double recall_level,

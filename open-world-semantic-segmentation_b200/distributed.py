@@ -1,0 +1,238 @@
+"""Pooled (full-set) exact AUROC / AUPR / FPR@95 across ranks -- SURVEY.md section 8(e).
+
+One process per GPU (``torch.distributed``, NCCL over NVLink).  Images shard per rank with no
+data-path collective; only the pooled ranking needs an exchange:
+
+  1. every rank turns its (conf, gt) pairs into packed keys and radix-sorts them locally;
+  2. G-1 splitters are chosen from an all-gathered regular sample of the sorted shards
+     (splitters have the positive bit cleared, so one score value never straddles two ranges);
+  3. exchange of the locally SORTED shards:
+       * ``mode="alltoall"`` (default): rank r receives only key range r from every peer
+         (NCCL all_to_all_single with uneven splits; each rank moves ~n/G keys);
+       * ``mode="allgather"``: every rank receives every sorted shard (the contract form of the
+         north star: "locally sorted shards merged through an NCCL allgather") and cuts its own
+         key range out of each;
+  4. the G sorted runs of a range are merged by one more local radix sort, the positives /
+     elements that precede the range are all-gathered (2 integers per rank) and the range is scanned
+     with those carried counts (``dml_ood_scan_range``);
+  5. the 48-byte partials are all-gathered and combined in rank order with exact integer /
+     fixed-order float64 arithmetic, so every rank returns bit-identical (auroc, aupr, fpr).
+
+The kernel-calling steps are isolated in ``CudaOps`` so that the exchange / carry / combine logic can
+be exercised on CPU with the gloo backend (tests/test_distributed.py injects a NumPy stand-in).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import ood
+
+SAMPLES_PER_RANK = 4096
+
+
+class CudaOps:
+    """The CUDA implementation of the local steps (the only product backend)."""
+
+    def __init__(self, device, workspace: Optional[ood.OodWorkspace] = None):
+        self.device = torch.device(device)
+        self.ws = workspace or ood.OodWorkspace(self.device)
+
+    # conf / gt -> packed keys (int32 view of the u32 keys), n_pos
+    def make_keys(self, conf, gt, out_labels, key_base):
+        from ._lib import check, lib, ptr, stream_ptr
+        n = conf.numel()
+        keys = self.ws.get("d_keys", 4 * max(n, 1)).view(torch.int32)[:n]
+        stats = self.ws.get("d_stats", 32).view(torch.int64)[:4]
+        g = gt.contiguous().view(-1)
+        with torch.cuda.device(self.device):
+            check(lib().dml_ood_keygen(ptr(conf.contiguous().view(-1)), None, 0, None,
+                                       ptr(g) if g.dtype == torch.uint8 else None, ptr(g) if g.dtype == torch.int64 else None,
+                                       ood.label_mask(out_labels), None, 0, key_base, 1, n, ptr(keys), ptr(stats),
+                                       None, None, None, 0.0, 0.0, stream_ptr(self.device)), "dml_ood_keygen")
+        return keys, stats
+
+    def sort(self, keys, tag="a"):
+        """returns a sorted int32 tensor (may alias ``keys`` or workspace memory)"""
+        from ._lib import check, lib, ptr, stream_ptr
+        n = keys.numel()
+        if n == 0:
+            return keys
+        nbytes = lib().dml_ood_workspace_bytes(1, n)
+        scratch = self.ws.get("d_sort_" + tag, nbytes)
+        out = C.c_void_p()
+        with torch.cuda.device(self.device):
+            check(lib().dml_ood_sort(ptr(keys), 1, n, 0, 32, ptr(scratch), scratch.numel(), C.byref(out),
+                                     stream_ptr(self.device)), "dml_ood_sort")
+        if out.value == keys.data_ptr():
+            return keys
+        off = out.value - scratch.data_ptr()
+        return scratch[off: off + 4 * n].view(torch.int32)
+
+    def lower_bound(self, sorted_keys, queries):
+        from ._lib import check, lib, ptr, stream_ptr
+        q = queries.to(self.device).contiguous()
+        pos = torch.empty(q.numel(), dtype=torch.int64, device=self.device)
+        with torch.cuda.device(self.device):
+            check(lib().dml_ood_lower_bound(ptr(sorted_keys), sorted_keys.numel(), ptr(q), q.numel(), ptr(pos),
+                                            stream_ptr(self.device)), "dml_ood_lower_bound")
+        return pos
+
+    def count_positive(self, keys):
+        from ._lib import check, lib, ptr, stream_ptr
+        out = torch.zeros(1, dtype=torch.int64, device=self.device)
+        with torch.cuda.device(self.device):
+            check(lib().dml_ood_count_positive(ptr(keys), keys.numel(), ptr(out), stream_ptr(self.device)),
+                  "dml_ood_count_positive")
+        return out
+
+    def sample(self, sorted_keys, n_samples):
+        n = sorted_keys.numel()
+        if n == 0:
+            return torch.full((n_samples,), -1, dtype=torch.int32, device=self.device)
+        idx = (torch.arange(n_samples, device=self.device, dtype=torch.float64) + 0.5) * (n / n_samples)
+        return sorted_keys[idx.long().clamp_(max=n - 1)]
+
+    def scan_range(self, sorted_keys, info, recall_level):
+        from ._lib import check, lib, ptr, stream_ptr
+        n = sorted_keys.numel()
+        partial = torch.empty(ood.PARTIAL_WORDS, dtype=torch.int64, device=self.device)
+        nbytes = lib().dml_ood_workspace_bytes(1, max(n, 1))
+        scratch = self.ws.get("d_scan", nbytes)
+        with torch.cuda.device(self.device):
+            check(lib().dml_ood_scan_range(ptr(sorted_keys), n, ptr(info), recall_level, ptr(scratch), scratch.numel(),
+                                           ptr(partial), stream_ptr(self.device)), "dml_ood_scan_range")
+        return partial
+
+    def empty_keys(self, n, tag):
+        return self.ws.get("d_recv_" + tag, 4 * max(n, 1)).view(torch.int32)[:n]
+
+
+def _as_unsigned(t: torch.Tensor) -> torch.Tensor:
+    """int32 bit patterns -> int64 values in [0, 2^32) (host-side ordering of a handful of samples)"""
+    return t.to(torch.int64) & 0xFFFFFFFF
+
+
+def choose_splitters(all_samples: torch.Tensor, world: int) -> torch.Tensor:
+    """all_samples: int64 unsigned key values gathered from every rank (-1 entries = empty shard).
+    Returns world+1 int64 boundaries b_0 = 0 < ... < b_world = 2^32 with the positive bit cleared."""
+    s = all_samples[all_samples >= 0]
+    s, _ = torch.sort(s)
+    bounds = [0]
+    for r in range(1, world):
+        if s.numel() == 0:
+            b = 0
+        else:
+            b = int(s[min(s.numel() - 1, (r * s.numel()) // world)].item()) & ~1
+        bounds.append(max(b, bounds[-1]))
+    bounds.append(1 << 32)
+    return torch.tensor(bounds, dtype=torch.int64)
+
+
+def pooled_measures(conf: torch.Tensor, gt: torch.Tensor, out_labels: Sequence[int] = (13,), *, group=None,
+                    recall_level: float = ood.RECALL_LEVEL_DEFAULT, mode: str = "alltoall", ops=None,
+                    workspace: Optional[ood.OodWorkspace] = None, key_base: int = ood.KEY_BASE_NONNEG):
+    """Exact pooled (auroc, aupr, fpr, info) over the (conf, gt) pairs of ALL ranks of ``group``.
+    ``conf`` must be non-negative (normalised maps); positives are gt in ``out_labels``; the ranked
+    score is -conf like anomaly/eval_ood_traditional.py:139-141.  Collective: every rank must call it."""
+    if mode not in ("alltoall", "allgather"):
+        raise ValueError("mode must be 'alltoall' or 'allgather'")
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    ops = ops or CudaOps(conf.device, workspace)
+    dev = conf.device
+
+    keys, stats = ops.make_keys(conf, gt, out_labels, key_base)
+    srt = ops.sort(keys, "local")
+    n_local = srt.numel()
+
+    # ---- splitters from a regular sample of every sorted shard -----------------------------------
+    smp = ops.sample(srt, SAMPLES_PER_RANK)
+    gathered = [torch.empty_like(smp) for _ in range(world)]
+    dist.all_gather(gathered, smp, group=group)
+    all_s = torch.cat(gathered).cpu()
+    # shards that are empty contribute the marker -1 (int32) -> drop them
+    vals = _as_unsigned(all_s)
+    vals[all_s == -1] = -1
+    bounds = choose_splitters(vals, world)                       # int64 [world+1]
+    q = (bounds[:-1] & 0xFFFFFFFF).to(torch.int64)
+    queries = torch.where(q >= (1 << 31), q - (1 << 32), q).to(torch.int32)   # bit patterns
+    cuts = ops.lower_bound(srt, queries)                          # [world] start of every range in my shard
+    cuts = torch.cat([cuts.cpu(), torch.tensor([n_local])])
+    send_counts = (cuts[1:] - cuts[:-1]).tolist()
+
+    # totals + stats (n_pos, n_nan, n_oow) in one tiny all_reduce
+    tot = torch.cat([stats[:3].to(torch.int64), torch.tensor([n_local], dtype=torch.int64, device=dev)])
+    dist.all_reduce(tot, group=group)
+    total_pos, n_nan, n_oow, total_n = [int(v) for v in tot.cpu().tolist()]
+    if n_nan:
+        raise ValueError("Input contains NaN.")
+    if n_oow:
+        raise ValueError("pooled_measures: conf must be non-negative (keys left the packed 31-bit window)")
+
+    # ---- exchange of the sorted shards ---------------------------------------------------------------
+    cnt = torch.tensor(send_counts, dtype=torch.int64, device=dev)
+    all_cnt = [torch.empty_like(cnt) for _ in range(world)]
+    dist.all_gather(all_cnt, cnt, group=group)
+    all_cnt = torch.stack(all_cnt).cpu()                          # [src, dst]
+    recv_counts = all_cnt[:, rank].tolist()
+    m = int(sum(recv_counts))
+    mine = ops.empty_keys(m, "range")
+    moved_bytes = 0
+    if mode == "alltoall":
+        dist.all_to_all_single(mine, srt, recv_counts, send_counts, group=group)
+        moved_bytes = 4 * (m - recv_counts[rank])
+    else:
+        sizes = all_cnt.sum(dim=1).tolist()
+        nmax = int(max(sizes)) if sizes else 0
+        pad = ops.empty_keys(nmax, "pad")
+        pad[:n_local].copy_(srt)
+        shards = [ops.empty_keys(nmax, f"shard{r}") for r in range(world)]
+        dist.all_gather(shards, pad, group=group)
+        off = 0
+        starts = torch.cat([torch.zeros(world, 1, dtype=torch.int64), torch.cumsum(all_cnt, dim=1)], dim=1)
+        for r in range(world):
+            a, c = int(starts[r, rank]), int(recv_counts[r])
+            mine[off: off + c].copy_(shards[r][a: a + c])
+            off += c
+        moved_bytes = 4 * int(sum(sizes) - sizes[rank])
+
+    # ---- merge (re-sort) my range, carry the counts that precede it, scan -----------------------------------
+    merged = ops.sort(mine, "merge")
+    pos_r = ops.count_positive(merged)
+    pr = torch.cat([pos_r.view(1), torch.tensor([m], dtype=torch.int64, device=dev)])
+    all_pr = [torch.empty_like(pr) for _ in range(world)]
+    dist.all_gather(all_pr, pr, group=group)
+    all_pr = torch.stack(all_pr).cpu()
+    pos_before = int(all_pr[:rank, 0].sum())
+    idx_before = int(all_pr[:rank, 1].sum())
+    info = torch.tensor([pos_before, idx_before, total_pos, total_n], dtype=torch.int64, device=dev)
+    partial = ops.scan_range(merged, info, recall_level)
+    parts = [torch.empty_like(partial) for _ in range(world)]
+    dist.all_gather(parts, partial, group=group)
+    auroc, aupr, fpr, groups = ood.combine_partials([p.cpu().numpy() for p in parts], total_pos, total_n)
+    return auroc, aupr, fpr, {"n_pos": total_pos, "n_neg": total_n - total_pos, "n_groups": groups, "range_keys": m,
+                               "exchanged_bytes": moved_bytes, "mode": mode}
+
+
+def mean_of_per_image(per_image_vals: torch.Tensor, group=None):
+    """The reference's aggregation (eval_ood_traditional.py:569,641): mean over images of the per-image
+    metrics, across ranks: one all_reduce of (sum_auroc, sum_aupr, sum_fpr, count).  ``per_image_vals``
+    is the float64 [n,>=3] device tensor of ``ood.eval_segments`` (NaN rows = skipped images)."""
+    v = per_image_vals[:, :3]
+    ok = ~torch.isnan(v[:, 0])
+    acc = torch.cat([torch.where(ok.unsqueeze(1), v, torch.zeros_like(v)).sum(0), ok.sum().to(v.dtype).view(1)])
+    dist.all_reduce(acc, group=group)
+    acc = acc.cpu()
+    cnt = float(acc[3])
+    return (float(acc[0]) / cnt, float(acc[1]) / cnt, float(acc[2]) / cnt, int(cnt)) if cnt else (float("nan"),) * 3 + (0,)
+
+
+def allreduce_counts(confusion: torch.Tensor, group=None) -> torch.Tensor:
+    """Sum of the per-rank confusion / class-count matrices (int64, exact)."""
+    dist.all_reduce(confusion, group=group)
+    return confusion

@@ -1,0 +1,76 @@
+"""NumPy stand-in for ``dml_b200.distributed.CudaOps`` (TEST DOUBLE, CPU only): the same local steps
+(pack keys, sort, cut, count, group scan) restated with NumPy so that the exchange / carry / combine logic of
+``pooled_measures`` can run under the gloo backend without a GPU."""
+import numpy as np
+import torch
+
+
+def _u(t):  # int32 bit patterns -> uint32 numpy
+    return t.numpy().view(np.uint32)
+
+
+class NumpyOps:
+    def make_keys(self, conf, gt, out_labels, key_base):
+        c = conf.contiguous().view(-1).numpy().astype(np.float32)
+        g = gt.contiguous().view(-1).numpy()
+        pos = np.isin(g, list(out_labels))
+        f = np.where(c == 0, np.float32(0), c)
+        bits = f.view(np.uint32)
+        srt = np.where(bits & 0x80000000, ~bits, bits | np.uint32(0x80000000)).astype(np.uint32)
+        n_nan = int(np.isnan(c).sum())
+        rel = (srt.astype(np.int64) - key_base)
+        oow = (rel < 0) | (rel >= (1 << 31))
+        keys = ((np.clip(rel, 0, (1 << 31) - 1).astype(np.uint64) << 1) | pos).astype(np.uint32)
+        stats = torch.tensor([int(pos.sum()), n_nan, int(oow.sum()), 0], dtype=torch.int64)
+        return torch.from_numpy(keys.view(np.int32).copy()), stats
+
+    def sort(self, keys, tag="a"):
+        return torch.from_numpy(np.sort(_u(keys)).view(np.int32).copy())
+
+    def lower_bound(self, sorted_keys, queries):
+        return torch.from_numpy(np.searchsorted(_u(sorted_keys), _u(queries.contiguous()), side="left").astype(np.int64))
+
+    def count_positive(self, keys):
+        return torch.tensor([int((_u(keys) & 1).sum())], dtype=torch.int64)
+
+    def sample(self, sorted_keys, n_samples):
+        n = sorted_keys.numel()
+        if n == 0:
+            return torch.full((n_samples,), -1, dtype=torch.int32)
+        idx = ((torch.arange(n_samples, dtype=torch.float64) + 0.5) * (n / n_samples)).long().clamp_(max=n - 1)
+        return sorted_keys[idx]
+
+    def scan_range(self, sorted_keys, info, recall_level):
+        k = _u(sorted_keys).astype(np.int64)
+        pos_before, idx_before, total_pos, total_n = [int(v) for v in info.tolist()]
+        out = np.zeros(6, np.int64)
+        out.view(np.float64)[2] = np.inf
+        out[3] = -1
+        if k.size:
+            score, lab = k >> 1, k & 1
+            ends = np.r_[np.nonzero(np.diff(score))[0], k.size - 1]
+            starts = np.r_[0, ends[:-1] + 1]
+            cpos = np.cumsum(lab)
+            tps = pos_before + cpos[ends]
+            n_so_far = idx_before + ends + 1
+            pos_g = cpos[ends] - np.r_[0, cpos[ends[:-1]]]
+            neg_g = (ends - starts + 1) - pos_g
+            num = int(sum(int(a) * (2 * int(b) - int(c)) for a, b, c in zip(neg_g, tps, pos_g)))
+            ap = 0.0
+            best = (np.inf, -1, 0)
+            for e, t, pg, ns in zip(ends, tps, pos_g, n_so_far):
+                if pg:
+                    ap += float(pg) * (float(t) / float(ns))
+                if t - pg < total_pos:
+                    d = abs(float(t) / float(total_pos) - recall_level)
+                    idx = idx_before + int(e)
+                    if d < best[0] or (d == best[0] and idx > best[1]):
+                        best = (d, idx, int(ns - t))
+            out.view(np.uint64)[0] = num
+            out.view(np.float64)[1] = ap
+            out.view(np.float64)[2] = best[0]
+            out[3], out[4], out[5] = best[1], best[2], len(ends)
+        return torch.from_numpy(out)
+
+    def empty_keys(self, n, tag):
+        return torch.empty(n, dtype=torch.int32)

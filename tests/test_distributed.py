@@ -1,0 +1,95 @@
+"""world_size-2 (and 3) gloo tests on CPU for the multi-GPU pooled metric: splitter choice, uneven all-to-all /
+all-gather exchange of sorted shards, carried counts, partial combination.  The kernel-calling steps are replaced by
+the NumPy test double (tests/np_ops.py); the result must equal the oracle on the concatenated data bit-for-bit."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import dml_oracle as O
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _make_shard(rank, case):
+    rng = np.random.default_rng(100 + rank)
+    n = {0: 5000, 1: 7001, 2: 123}[rank]
+    if case == "empty_rank" and rank == 1:
+        n = 0
+    conf = rng.random(n).astype(np.float32)
+    if case in ("ties", "empty_rank"):
+        conf = (np.round(conf * 20) / 20).astype(np.float32)      # the same 21 values on every rank
+    conf[rng.random(n) < 0.1] = 1.0                                # clamp plateau shared by all ranks
+    gt = rng.integers(0, 14, n).astype(np.int64)
+    gt[rng.random(n) < 0.7] = 2
+    if case == "skewed":
+        conf = (conf * (0.2 + 0.4 * rank)).astype(np.float32)     # shards cover different score ranges
+    return conf, gt
+
+
+def _worker(rank, world, port, case, mode, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from dml_b200 import distributed as D
+        from tests.np_ops import NumpyOps
+        conf, gt = _make_shard(rank, case)
+        a, p, f, info = D.pooled_measures(torch.from_numpy(conf), torch.from_numpy(gt), (13,), mode=mode, ops=NumpyOps())
+        vals = torch.tensor([[0.5 + 0.1 * rank, 0.2, 0.3], [float("nan")] * 3, [0.7, 0.4, 0.1]], dtype=torch.float64)
+        mean = D.mean_of_per_image(vals)
+        conf_m = torch.full((3, 3), rank + 1, dtype=torch.int64)
+        D.allreduce_counts(conf_m)
+        q.put((rank, a, p, f, info, mean, conf_m.tolist()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,case,mode", [(2, "plain", "alltoall"), (2, "ties", "alltoall"), (2, "ties", "allgather"),
+                                             (3, "skewed", "alltoall"), (3, "empty_rank", "allgather"), (2, "empty_rank", "alltoall")])
+def test_pooled_measures_gloo(world, case, mode):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, case, mode, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    shards = [_make_shard(r, case) for r in range(world)]
+    conf = np.concatenate([s[0] for s in shards])
+    gt = np.concatenate([s[1] for s in shards])
+    ref = O.eval_ood_measure(conf, gt, (13,))
+    first = sorted(results)[0]
+    for r in sorted(results):
+        assert (r[1], r[2], r[3]) == (first[1], first[2], first[3]), "ranks must agree bit-for-bit"
+        np.testing.assert_allclose([r[1], r[2], r[3]], ref, rtol=0, atol=1e-12)
+        assert r[4]["n_pos"] == int((gt == 13).sum()) and r[4]["n_neg"] == int((gt != 13).sum())
+        assert r[4]["n_groups"] == np.unique(conf).size
+        # per-image mean across ranks: NaN rows skipped, 2 images per rank counted
+        exp = np.mean([[0.5 + 0.1 * k, 0.2, 0.3] for k in range(world)] + [[0.7, 0.4, 0.1]] * world, axis=0)
+        np.testing.assert_allclose(r[5][:3], exp, rtol=1e-12)
+        assert r[5][3] == 2 * world
+        assert r[6] == [[sum(range(1, world + 1))] * 3] * 3
+    assert sum(r[4]["range_keys"] for r in results) == conf.size
+
+
+def test_choose_splitters_properties():
+    from dml_b200.distributed import choose_splitters
+    s = torch.tensor([5, 9, 9, 9, 9, 9, 9, 100, 101, 3000, -1, -1], dtype=torch.int64)
+    b = choose_splitters(s, 4)
+    assert b[0] == 0 and b[-1] == 1 << 32 and (b[1:] >= b[:-1]).all()
+    assert all(int(v) % 2 == 0 for v in b[:-1])          # positive bit cleared: a score never straddles ranges
+    assert choose_splitters(torch.tensor([-1, -1], dtype=torch.int64), 2).tolist() == [0, 0, 1 << 32]
