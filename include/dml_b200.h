@@ -225,8 +225,12 @@ DML_API int dml_ood_eval_segments(uint32_t* keys, const long long* seg_stats, in
  * pointer-to-pointer) receives the device buffer holding the result (keys, or inside workspace).
  * dml_ood_scan_range: group scan over an already sorted key range that starts on a score-group
  * boundary.  range_info (device, 4 int64) = (pos_before, idx_before, total_pos, total_n) of the
- * global ranking.  partial_out (device, 48 bytes) = { u64 auroc_num; f64 ap_sum; f64 best_dist;
- * i64 best_idx; i64 best_fps; i64 n_groups } -- ranges combine by (+, +, argmin(dist, -idx), +). */
+ * global ranking.  partial_out (device, 80 bytes) = { u64 auroc_num; f64 ap_sum; i64 a_idx, a_tps, a_fps;
+ * i64 b_tps, b_idx, b_fps; i64 n_groups; i64 reserved }: a = the last group whose cumulative positives tps
+ * stay <= T* (the largest tps with float64 recall tps/P <= recall_level; a_idx = -1: none), b = the smallest
+ * tps > T* and the latest group having it (b_tps = INT64_MAX: none).  Ranges combine by
+ * (+, +, max idx, (min tps, max idx), +); FPR = fps of whichever of a / b has the smaller
+ * |tps/P - recall_level| in float64 (tie -> b), divided by N. */
 DML_API int dml_ood_sort(uint32_t* keys, int32_t n_seg, int64_t seg_len, int32_t begin_bit, int32_t end_bit,
                  void* workspace, size_t workspace_bytes, uint32_t** sorted_out, dml_stream_t stream);
 /* positions[j] = first index with sorted_keys[i] >= queries[j] (cuts a sorted shard at the range splitters);

@@ -214,14 +214,44 @@ __device__ __forceinline__ Agg agg_shfl_up(const Agg& a, int o) {
 struct Carry {  // running state across tiles (64-bit)
   unsigned long long pos, spos, slen;
 };
+// Per-tile / per-range partial result (10 x 8 bytes; the layout is part of the C ABI, see
+// dml_ood_scan_range).  FPR candidates are kept in integers: with T* = the largest tps whose
+// float64 recall tps/P is <= recall_level, |tps/P - recall_level| is non-increasing up to T* and
+// non-decreasing after it, so the reference's argmin (ties -> later group) is one of
+//   a = the LAST group with tps <= T*,   b = the smallest tps > T*, latest group having it.
 struct TilePartial {
   unsigned long long auroc_num;
   double ap_sum;
-  double best_dist;
-  long long best_idx;
-  long long best_fps;
+  long long a_idx, a_tps, a_fps;   // a_idx = -1: none
+  long long b_tps, b_idx, b_fps;   // b_tps = LLONG_MAX: none
   long long n_groups;
+  long long reserved;
 };
+constexpr long long NO_B = 0x7fffffffffffffffll;
+
+__device__ __forceinline__ void partial_init(TilePartial& t) {
+  t.auroc_num = 0ull; t.ap_sum = 0.0;
+  t.a_idx = -1; t.a_tps = 0; t.a_fps = 0;
+  t.b_tps = NO_B; t.b_idx = -1; t.b_fps = 0;
+  t.n_groups = 0; t.reserved = 0;
+}
+__device__ __forceinline__ void partial_merge(TilePartial& a, const TilePartial& b) {
+  a.auroc_num += b.auroc_num;
+  a.ap_sum += b.ap_sum;
+  a.n_groups += b.n_groups;
+  if (b.a_idx > a.a_idx) { a.a_idx = b.a_idx; a.a_tps = b.a_tps; a.a_fps = b.a_fps; }
+  if (b.b_tps < a.b_tps || (b.b_tps == a.b_tps && b.b_idx > a.b_idx)) { a.b_tps = b.b_tps; a.b_idx = b.b_idx; a.b_fps = b.b_fps; }
+}
+// largest integer t in [0, P] with (double)t / (double)P <= r  (float64 division, like NumPy's recall)
+__device__ __forceinline__ long long recall_threshold(long long P, double r) {
+  if (P <= 0) return 0;
+  const double dP = (double)P;
+  double g = floor(r * dP);
+  long long t = g < 0.0 ? 0 : (g > dP ? P : (long long)g);
+  while (t < P && (double)(t + 1) / dP <= r) ++t;
+  while (t > 0 && (double)t / dP > r) --t;
+  return t;
+}
 
 struct RangeInfo {  // device-resident description of one scan range (segment)
   long long pos_before;  // positives ranked before this range
@@ -361,10 +391,6 @@ __global__ void __launch_bounds__(CARRY_THREADS) scan_carry_kernel(const Agg* __
   }
 }
 
-__device__ __forceinline__ bool best_better(double da, long long ia, double db, long long ib) {
-  return da < db || (da == db && ia > ib);
-}
-
 // phase 3: per-tile group contributions
 __global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(const uint32_t* __restrict__ keys, long long seg_len,
                                                                   int tiles_per_seg, const Carry* __restrict__ tile_carry,
@@ -373,12 +399,16 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(const uint32_t
   __shared__ uint32_t s_keys[SCAN_TILE + SCAN_TILE / 16 + 2];
   __shared__ Agg s_w[SCAN_WARPS];
   __shared__ TilePartial s_p[SCAN_WARPS];
+  __shared__ long long s_tstar;
   const int seg = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const uint32_t* k = keys + (size_t)seg * (size_t)seg_len;
   const long long tile_off = (long long)tile * SCAN_TILE;
   const long long first = tile_off + (long long)tid * SCAN_ITEMS;
+  const RangeInfo ri = info[seg];
+  if (tid == 0) s_tstar = recall_threshold(ri.total_pos, recall_level);
   TileKeys tk;
-  load_tile(k, seg_len, tile_off, s_keys, tk);
+  load_tile(k, seg_len, tile_off, s_keys, tk);   // contains the __syncthreads that publishes s_tstar
+  const long long tstar = s_tstar;
   const Agg mine = thread_aggregate(tk, seg_len, first);
   // exclusive block scan of the thread aggregates
   Agg incl = mine;
@@ -396,18 +426,13 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(const uint32_t
   excl = agg_combine(wpre, excl);
 
   const Carry tc = tile_carry[(size_t)seg * tiles_per_seg + tile];
-  unsigned long long P = tc.pos + excl.pos;
-  unsigned long long spos = excl.head ? excl.spos : tc.spos + excl.spos;
-  unsigned long long slen = excl.head ? excl.slen : tc.slen + excl.slen;
+  long long P = (long long)(tc.pos + excl.pos);                       // positives ranked so far (inclusive)
+  long long spos = (long long)(excl.head ? excl.spos : tc.spos + excl.spos);
+  long long slen = (long long)(excl.head ? excl.slen : tc.slen + excl.slen);
+  const long long Ptot = ri.total_pos;
 
-  const RangeInfo ri = info[seg];
-  const unsigned long long Ptot = (unsigned long long)ri.total_pos;
-  const double dP = (double)ri.total_pos;
-
-  unsigned long long auroc = 0ull;
-  double ap = 0.0;
-  double bdist = __longlong_as_double(0x7ff0000000000000ll);  // +inf
-  long long bidx = -1, bfps = 0, ngroups = 0;
+  TilePartial acc;
+  partial_init(acc);
 
   uint32_t prev = tk.prev;
   bool have_prev = tk.has_prev;
@@ -417,7 +442,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(const uint32_t
     if (gi < seg_len) {
       const uint32_t key = tk.k[j];
       const bool head = !have_prev || ((key >> 1) != (prev >> 1));
-      const unsigned p = key & 1u;
+      const long long p = (long long)(key & 1u);
       if (head) { spos = 0; slen = 0; }
       P += p; spos += p; slen += 1;
       prev = key; have_prev = true;
@@ -429,72 +454,58 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(const uint32_t
         endg = (nk >> 1) != (key >> 1);
       }
       if (endg) {
-        const unsigned long long n_so_far = (unsigned long long)(ri.idx_before + gi + 1);
-        const unsigned long long neg_g = slen - spos;
-        const unsigned long long fps = n_so_far - P;
-        auroc += neg_g * (2ull * P - spos);
-        if (spos) ap += (double)spos * ((double)P / (double)n_so_far);
-        if (P - spos < Ptot) {
-          const double dist = fabs((double)P / dP - recall_level);
-          const long long idx = ri.idx_before + gi;
-          if (best_better(dist, idx, bdist, bidx)) { bdist = dist; bidx = idx; bfps = (long long)fps; }
+        const long long idx = ri.idx_before + gi;
+        const long long n_so_far = idx + 1;
+        const long long fps = n_so_far - P;
+        acc.auroc_num += (unsigned long long)((slen - spos) * (2 * P - spos));
+        if (spos) acc.ap_sum += (double)spos * ((double)P / (double)n_so_far);   // rare: positives are few
+        if (P - spos < Ptot) {                                               // groups up to the first with full recall
+          if (P <= tstar) {
+            if (idx > acc.a_idx) { acc.a_idx = idx; acc.a_tps = P; acc.a_fps = fps; }
+          } else if (P < acc.b_tps || (P == acc.b_tps && idx > acc.b_idx)) {
+            acc.b_tps = P; acc.b_idx = idx; acc.b_fps = fps;
+          }
         }
-        ++ngroups;
+        ++acc.n_groups;
       }
     }
   }
   // block reduction (fixed order)
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
-    auroc += __shfl_down_sync(0xffffffffu, auroc, o);
-    ap += __shfl_down_sync(0xffffffffu, ap, o);
-    ngroups += __shfl_down_sync(0xffffffffu, ngroups, o);
-    const double od = __shfl_down_sync(0xffffffffu, bdist, o);
-    const long long oi = __shfl_down_sync(0xffffffffu, bidx, o);
-    const long long of = __shfl_down_sync(0xffffffffu, bfps, o);
-    if (best_better(od, oi, bdist, bidx)) { bdist = od; bidx = oi; bfps = of; }
+    TilePartial other;
+    other.auroc_num = __shfl_down_sync(0xffffffffu, acc.auroc_num, o);
+    other.ap_sum = __shfl_down_sync(0xffffffffu, acc.ap_sum, o);
+    other.a_idx = __shfl_down_sync(0xffffffffu, acc.a_idx, o);
+    other.a_tps = __shfl_down_sync(0xffffffffu, acc.a_tps, o);
+    other.a_fps = __shfl_down_sync(0xffffffffu, acc.a_fps, o);
+    other.b_tps = __shfl_down_sync(0xffffffffu, acc.b_tps, o);
+    other.b_idx = __shfl_down_sync(0xffffffffu, acc.b_idx, o);
+    other.b_fps = __shfl_down_sync(0xffffffffu, acc.b_fps, o);
+    other.n_groups = __shfl_down_sync(0xffffffffu, acc.n_groups, o);
+    partial_merge(acc, other);
   }
-  if (lane == 0) {
-    TilePartial t;
-    t.auroc_num = auroc; t.ap_sum = ap; t.best_dist = bdist; t.best_idx = bidx; t.best_fps = bfps; t.n_groups = ngroups;
-    s_p[w] = t;
-  }
+  if (lane == 0) s_p[w] = acc;
   __syncthreads();
   if (tid == 0) {
     TilePartial t = s_p[0];
-    for (int i = 1; i < SCAN_WARPS; ++i) {
-      t.auroc_num += s_p[i].auroc_num;
-      t.ap_sum += s_p[i].ap_sum;
-      t.n_groups += s_p[i].n_groups;
-      if (best_better(s_p[i].best_dist, s_p[i].best_idx, t.best_dist, t.best_idx)) {
-        t.best_dist = s_p[i].best_dist; t.best_idx = s_p[i].best_idx; t.best_fps = s_p[i].best_fps;
-      }
-    }
+    for (int i = 1; i < SCAN_WARPS; ++i) partial_merge(t, s_p[i]);
     partials[(size_t)seg * tiles_per_seg + tile] = t;
   }
 }
 
 // phase 4: fixed-order reduction of the tile partials of each segment
 constexpr int FIN_THREADS = 256;
-__device__ __forceinline__ void partial_merge(TilePartial& a, const TilePartial& b) {
-  a.auroc_num += b.auroc_num;
-  a.ap_sum += b.ap_sum;
-  a.n_groups += b.n_groups;
-  if (best_better(b.best_dist, b.best_idx, a.best_dist, a.best_idx)) {
-    a.best_dist = b.best_dist; a.best_idx = b.best_idx; a.best_fps = b.best_fps;
-  }
-}
 __global__ void __launch_bounds__(FIN_THREADS) scan_finalize_kernel(const TilePartial* __restrict__ partials, int tiles_per_seg,
                                                                     const RangeInfo* __restrict__ info,
                                                                     const unsigned long long* __restrict__ seg_stats,
-                                                                    dml_ood_result* __restrict__ results,
+                                                                    double recall_level, dml_ood_result* __restrict__ results,
                                                                     TilePartial* __restrict__ range_partials) {
   __shared__ TilePartial s_t[FIN_THREADS];
   const int seg = blockIdx.x, tid = threadIdx.x;
   const TilePartial* pp = partials + (size_t)seg * tiles_per_seg;
   TilePartial t;
-  t.auroc_num = 0ull; t.ap_sum = 0.0; t.best_dist = __longlong_as_double(0x7ff0000000000000ll);
-  t.best_idx = -1; t.best_fps = 0; t.n_groups = 0;
+  partial_init(t);
   // contiguous chunk per thread => the same summation order regardless of scheduling
   const int per = (tiles_per_seg + FIN_THREADS - 1) / FIN_THREADS;
   const int b = tid * per;
@@ -525,7 +536,11 @@ __global__ void __launch_bounds__(FIN_THREADS) scan_finalize_kernel(const TilePa
       if (ri.total_pos > 0 && o.n_neg > 0) {
         o.auroc = (double)r.auroc_num / (2.0 * P * N);
         o.aupr = r.ap_sum / P;
-        o.fpr = (double)r.best_fps / N;
+        // |recall - level| of the two candidates in float64, ties -> the later group (b)
+        const double inf = __longlong_as_double(0x7ff0000000000000ll);
+        const double da = r.a_idx >= 0 ? fabs((double)r.a_tps / P - recall_level) : inf;
+        const double db = r.b_tps != NO_B ? fabs((double)r.b_tps / P - recall_level) : inf;
+        o.fpr = (double)(db <= da ? r.b_fps : r.a_fps) / N;
       } else {
         const double nan = __longlong_as_double(0x7ff8000000000000ll);
         o.auroc = o.aupr = o.fpr = nan;
@@ -603,7 +618,7 @@ int run_scan(const uint32_t* sorted, const MetricsPlan& m, unsigned char* ws, co
   DML_LAUNCH_CHECK();
   scan_apply_kernel<<<grid, SCAN_THREADS, 0, stream>>>(sorted, m.sort.seg_len, m.tiles_per_seg, carry, info, recall_level, partial);
   DML_LAUNCH_CHECK();
-  scan_finalize_kernel<<<m.sort.n_seg, FIN_THREADS, 0, stream>>>(partial, m.tiles_per_seg, info, seg_stats, results, range_partials);
+  scan_finalize_kernel<<<m.sort.n_seg, FIN_THREADS, 0, stream>>>(partial, m.tiles_per_seg, info, seg_stats, recall_level, results, range_partials);
   DML_LAUNCH_CHECK();
   return DML_OK;
 }

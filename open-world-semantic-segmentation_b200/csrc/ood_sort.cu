@@ -117,61 +117,95 @@ struct LbTraits<unsigned long long> {
   static constexpr int FLAG_SHIFT = 62;
 };
 
+// Peer mask for one 8-bit digit in exactly 4 SASS instructions per bit (test bit -> predicate, VOTE,
+// predicated NOT, AND); nvcc's own code for the C++ form above spends 6.
+__device__ __forceinline__ unsigned match8_full(uint32_t d) {
+  unsigned peers;
+  asm volatile(
+      "{\n"
+      " .reg .pred p;\n"
+      " .reg .b32 v, t;\n"
+      " and.b32 t, %1, 1;   setp.ne.u32 p, t, 0; vote.sync.ballot.b32 %0, p, 0xffffffff; @!p not.b32 %0, %0;\n"
+      " and.b32 t, %1, 2;   setp.ne.u32 p, t, 0; vote.sync.ballot.b32 v, p, 0xffffffff; @!p not.b32 v, v; and.b32 %0, %0, v;\n"
+      " and.b32 t, %1, 4;   setp.ne.u32 p, t, 0; vote.sync.ballot.b32 v, p, 0xffffffff; @!p not.b32 v, v; and.b32 %0, %0, v;\n"
+      " and.b32 t, %1, 8;   setp.ne.u32 p, t, 0; vote.sync.ballot.b32 v, p, 0xffffffff; @!p not.b32 v, v; and.b32 %0, %0, v;\n"
+      " and.b32 t, %1, 16;  setp.ne.u32 p, t, 0; vote.sync.ballot.b32 v, p, 0xffffffff; @!p not.b32 v, v; and.b32 %0, %0, v;\n"
+      " and.b32 t, %1, 32;  setp.ne.u32 p, t, 0; vote.sync.ballot.b32 v, p, 0xffffffff; @!p not.b32 v, v; and.b32 %0, %0, v;\n"
+      " and.b32 t, %1, 64;  setp.ne.u32 p, t, 0; vote.sync.ballot.b32 v, p, 0xffffffff; @!p not.b32 v, v; and.b32 %0, %0, v;\n"
+      " and.b32 t, %1, 128; setp.ne.u32 p, t, 0; vote.sync.ballot.b32 v, p, 0xffffffff; @!p not.b32 v, v; and.b32 %0, %0, v;\n"
+      "}\n"
+      : "=r"(peers)
+      : "r"(d));
+  return peers;
+}
+
+// byte `sel` (0..3) of k: the digit when the shift is a multiple of 8 (PRMT, one instruction)
+__device__ __forceinline__ uint32_t digit_of(uint32_t k, int shift, uint32_t prmt_sel) {
+  (void)shift;
+  return __byte_perm(k, 0u, prmt_sel);
+}
+
 template <typename LB>
-__global__ void __launch_bounds__(SORT_THREADS) onesweep_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out,
-                                                                long long seg_len, int tiles_per_seg, int shift, int pass,
-                                                                const uint32_t* __restrict__ ghist_excl, LB* lookback,
-                                                                uint32_t* tickets) {
+__global__ void __launch_bounds__(SORT_THREADS, 3) onesweep_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out,
+                                                                   long long seg_len, int tiles_per_seg, int shift, int pass,
+                                                                   const uint32_t* __restrict__ ghist_excl, LB* lookback,
+                                                                   uint32_t* tickets) {
   using T = LbTraits<LB>;
   __shared__ uint32_t s_whist[SORT_WARPS][RADIX];
   __shared__ uint32_t s_keys[SORT_TILE];
-  __shared__ unsigned long long s_gbase[RADIX];
+  __shared__ uint32_t s_gbase[RADIX];   // global index of the tile's first key of each digit, minus its tile position
   __shared__ uint32_t s_scan[SORT_WARPS];
   __shared__ int s_tile;
 
   const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
   const int seg = blockIdx.y;
   if (tid == 0) s_tile = (int)atomicAdd(tickets + seg, 1u);
-  for (int i = tid; i < SORT_WARPS * RADIX; i += SORT_THREADS) (&s_whist[0][0])[i] = 0u;
+#pragma unroll
+  for (int i = 0; i < SORT_WARPS; ++i) s_whist[i][tid] = 0u;
   __syncthreads();
   const int tile = s_tile;
   const size_t seg_base = (size_t)seg * (size_t)seg_len;
   const long long tile_off = (long long)tile * SORT_TILE;
   const long long rem = seg_len - tile_off;
   const int nvalid = rem >= SORT_TILE ? SORT_TILE : (int)rem;
+  const bool full = nvalid == SORT_TILE;
+  const uint32_t sel = 0x4440u + (uint32_t)(shift >> 3);  // shift is a multiple of 8
 
   // ---- load (warp-striped inside the warp's contiguous slice => LSD-stable order) ----------
   uint32_t key[SORT_ITEMS];
   uint32_t rank[SORT_ITEMS];
-  const int wbase = w * 32 * SORT_ITEMS;
-  const uint32_t* src = in + seg_base + tile_off;
-#pragma unroll
-  for (int i = 0; i < SORT_ITEMS; ++i) {
-    const int idx = wbase + i * 32 + lane;
-    key[i] = idx < nvalid ? src[idx] : 0xffffffffu;
-  }
-  // ---- rank within warp ----------------------------------------------------------------------
-  // phase 1 (pure ALU, full ILP across items): peer masks; phase 2: the group leader advances the
-  // warp-private running count of its digit and broadcasts the group's base rank.
-  const unsigned lt = lanemask_lt();
   unsigned peers[SORT_ITEMS];
+  const int wbase = w * 32 * SORT_ITEMS;
+  const uint32_t* src = in + seg_base + tile_off + wbase + lane;
+  if (full) {
 #pragma unroll
-  for (int i = 0; i < SORT_ITEMS; ++i) {
-    const int idx = wbase + i * 32 + lane;
-    peers[i] = match_digit8((key[i] >> shift) & (RADIX - 1), idx < nvalid);
-  }
+    for (int i = 0; i < SORT_ITEMS; ++i) key[i] = src[i * 32];
 #pragma unroll
-  for (int i = 0; i < SORT_ITEMS; ++i) {
-    const uint32_t d = (key[i] >> shift) & (RADIX - 1);
-    const int leader = __ffs(peers[i]) - 1;  // -1 for invalid lanes
-    uint32_t c = 0;
-    if (lane == leader) {
-      c = s_whist[w][d];
-      s_whist[w][d] = c + (uint32_t)__popc(peers[i]);
+    for (int i = 0; i < SORT_ITEMS; ++i) peers[i] = match8_full(digit_of(key[i], shift, sel));
+  } else {
+#pragma unroll
+    for (int i = 0; i < SORT_ITEMS; ++i) key[i] = (wbase + i * 32 + lane) < nvalid ? src[i * 32] : 0xffffffffu;
+#pragma unroll
+    for (int i = 0; i < SORT_ITEMS; ++i) {
+      const bool valid = (wbase + i * 32 + lane) < nvalid;
+      const unsigned vm = __ballot_sync(0xffffffffu, valid);
+      const unsigned pm = match8_full(digit_of(key[i], shift, sel));
+      peers[i] = valid ? (pm & vm) : 0u;
     }
+  }
+  // ---- rank within warp: every member reads the warp-private running count of its digit, the group's
+  //      lowest lane advances it by the group size ------------------------------------------------
+  const unsigned lt = lanemask_lt();
+  uint32_t* myhist = s_whist[w];
+#pragma unroll
+  for (int i = 0; i < SORT_ITEMS; ++i) {
+    const uint32_t d = digit_of(key[i], shift, sel);
+    const uint32_t below = (uint32_t)__popc(peers[i] & lt);
+    const uint32_t c = myhist[d];
     __syncwarp();
-    c = __shfl_sync(0xffffffffu, c, leader < 0 ? 0 : leader);
-    rank[i] = c + (uint32_t)__popc(peers[i] & lt);
+    if (below == 0 && peers[i] != 0) myhist[d] = c + (uint32_t)__popc(peers[i]);
+    __syncwarp();
+    rank[i] = c + below;
   }
   __syncthreads();
 
@@ -213,7 +247,8 @@ __global__ void __launch_bounds__(SORT_THREADS) onesweep_kernel(const uint32_t* 
     }
     lb[tid] = (LB)(excl + run) | T::INCL;
   }
-  s_gbase[tid] = (unsigned long long)ghist_excl[((size_t)seg * MAX_PASSES + pass) * RADIX + tid] + excl - dbase;
+  // segment-relative index (seg_len < 2^32): wraps correctly in 32-bit arithmetic
+  s_gbase[tid] = ghist_excl[((size_t)seg * MAX_PASSES + pass) * RADIX + tid] + (uint32_t)excl - dbase;
 #pragma unroll
   for (int ww = 0; ww < SORT_WARPS; ++ww) s_whist[ww][tid] += dbase;
   __syncthreads();
@@ -221,10 +256,9 @@ __global__ void __launch_bounds__(SORT_THREADS) onesweep_kernel(const uint32_t* 
   // ---- local scatter into digit order, then coalesced runs to global -----------------------------
 #pragma unroll
   for (int i = 0; i < SORT_ITEMS; ++i) {
-    const int idx = wbase + i * 32 + lane;
-    if (idx < nvalid) {
-      const uint32_t d = (key[i] >> shift) & (RADIX - 1);
-      s_keys[s_whist[w][d] + rank[i]] = key[i];
+    if (full || (wbase + i * 32 + lane) < nvalid) {
+      const uint32_t d = digit_of(key[i], shift, sel);
+      s_keys[myhist[d] + rank[i]] = key[i];
     }
   }
   __syncthreads();
@@ -232,10 +266,10 @@ __global__ void __launch_bounds__(SORT_THREADS) onesweep_kernel(const uint32_t* 
 #pragma unroll
   for (int j = 0; j < SORT_ITEMS; ++j) {
     const int pos = j * SORT_THREADS + tid;
-    if (pos < nvalid) {
+    if (full || pos < nvalid) {
       const uint32_t k = s_keys[pos];
-      const uint32_t d = (k >> shift) & (RADIX - 1);
-      dst[s_gbase[d] + (unsigned long long)pos] = k;
+      const uint32_t d = digit_of(k, shift, sel);
+      dst[(uint32_t)(s_gbase[d] + (uint32_t)pos)] = k;
     }
   }
 }

@@ -214,7 +214,7 @@ def pooled_measures(conf: torch.Tensor, gt: torch.Tensor, out_labels: Sequence[i
     partial = ops.scan_range(merged, info, recall_level)
     parts = [torch.empty_like(partial) for _ in range(world)]
     dist.all_gather(parts, partial, group=group)
-    auroc, aupr, fpr, groups = ood.combine_partials([p.cpu().numpy() for p in parts], total_pos, total_n)
+    auroc, aupr, fpr, groups = ood.combine_partials([p.cpu().numpy() for p in parts], total_pos, total_n, recall_level)
     return auroc, aupr, fpr, {"n_pos": total_pos, "n_neg": total_n - total_pos, "n_groups": groups, "range_keys": m,
                                "exchanged_bytes": moved_bytes, "mode": mode}
 

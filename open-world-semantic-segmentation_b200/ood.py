@@ -17,7 +17,8 @@ from ._lib import OOD_RESULT_WORDS, check, lib, ptr, require_cuda, stream_ptr
 
 RECALL_LEVEL_DEFAULT = 0.95       # anomaly/anom_utils.py:4
 KEY_BASE_NONNEG = 0x80000000      # sortable image of +0.0: any conf >= 0 fits the 31-bit window
-PARTIAL_WORDS = 6                 # u64 auroc_num, f64 ap_sum, f64 best_dist, i64 best_idx, i64 best_fps, i64 n_groups
+PARTIAL_WORDS = 10                # u64 auroc_num, f64 ap_sum, i64 a_idx,a_tps,a_fps, b_tps,b_idx,b_fps, n_groups, reserved
+NO_B = (1 << 63) - 1
 
 
 def label_mask(out_labels: Iterable[int]) -> int:
@@ -140,25 +141,33 @@ def _scan_sorted_range(sorted_keys_ptr: int, n: int, pos_before: int, idx_before
     return partial.cpu().numpy()
 
 
-def combine_partials(partials: Sequence[np.ndarray], total_pos: int, total_n: int):
-    """Combine per-range partial tuples (in ranking order) into (auroc, aupr, fpr, n_groups).
-    Sums are exact integers / fixed-order float64 adds, so every rank computes identical bits."""
+def combine_partials(partials: Sequence[np.ndarray], total_pos: int, total_n: int,
+                     recall_level: float = RECALL_LEVEL_DEFAULT):
+    """Combine per-range partial tuples (see ``dml_ood_scan_range``) into (auroc, aupr, fpr, n_groups).
+    Sums are exact integers / fixed-order float64 adds and the FPR choice compares two float64
+    recalls, so every rank computes identical bits."""
     num = 0
     ap = 0.0
-    best = (np.inf, -1, 0)
+    a = (-1, 0, 0)          # idx, tps, fps
+    b = (NO_B, -1, 0)       # tps, idx, fps
     groups = 0
     for p in partials:
         p = np.asarray(p, dtype=np.int64)
         num += int(p.view(np.uint64)[0])
         ap += float(p.view(np.float64)[1])
-        dist, idx, fps = float(p.view(np.float64)[2]), int(p[3]), int(p[4])
-        if dist < best[0] or (dist == best[0] and idx > best[1]):
-            best = (dist, idx, fps)
-        groups += int(p[5])
+        if int(p[2]) > a[0]:
+            a = (int(p[2]), int(p[3]), int(p[4]))
+        if int(p[5]) < b[0] or (int(p[5]) == b[0] and int(p[6]) > b[1]):
+            b = (int(p[5]), int(p[6]), int(p[7]))
+        groups += int(p[8])
     n_neg = total_n - total_pos
     if total_pos == 0 or n_neg == 0:
         return float("nan"), float("nan"), float("nan"), groups
-    return num / (2.0 * total_pos * n_neg), ap / total_pos, best[2] / n_neg, groups
+    P = float(total_pos)
+    da = abs(a[1] / P - recall_level) if a[0] >= 0 else float("inf")
+    db = abs(b[0] / P - recall_level) if b[0] != NO_B else float("inf")
+    fps = b[2] if db <= da else a[2]
+    return num / (2.0 * total_pos * n_neg), ap / total_pos, fps / n_neg, groups
 
 
 def measures_from_scores(scores: torch.Tensor, positive: torch.Tensor, recall_level: float = RECALL_LEVEL_DEFAULT,
@@ -212,5 +221,5 @@ def measures_from_scores(scores: torch.Tensor, positive: torch.Tensor, recall_le
                                                recall_level, ws, dev))
             pos_before += int(po.sum().item())
             idx_before += m
-        a, p, f, _ = combine_partials(partials, total_pos, n)
+        a, p, f, _ = combine_partials(partials, total_pos, n, recall_level)
         return a, p, f

@@ -43,9 +43,16 @@ class NumpyOps:
     def scan_range(self, sorted_keys, info, recall_level):
         k = _u(sorted_keys).astype(np.int64)
         pos_before, idx_before, total_pos, total_n = [int(v) for v in info.tolist()]
-        out = np.zeros(6, np.int64)
-        out.view(np.float64)[2] = np.inf
-        out[3] = -1
+        out = np.zeros(10, np.int64)
+        out[2], out[5], out[6] = -1, (1 << 63) - 1, -1
+        # T* = largest t with float64 t/P <= recall_level
+        tstar = 0
+        if total_pos > 0:
+            tstar = min(total_pos, max(0, int(np.floor(recall_level * total_pos))))
+            while tstar < total_pos and (tstar + 1) / total_pos <= recall_level:
+                tstar += 1
+            while tstar > 0 and tstar / total_pos > recall_level:
+                tstar -= 1
         if k.size:
             score, lab = k >> 1, k & 1
             ends = np.r_[np.nonzero(np.diff(score))[0], k.size - 1]
@@ -57,19 +64,24 @@ class NumpyOps:
             neg_g = (ends - starts + 1) - pos_g
             num = int(sum(int(a) * (2 * int(b) - int(c)) for a, b, c in zip(neg_g, tps, pos_g)))
             ap = 0.0
-            best = (np.inf, -1, 0)
+            a = (-1, 0, 0)
+            b = ((1 << 63) - 1, -1, 0)
             for e, t, pg, ns in zip(ends, tps, pos_g, n_so_far):
+                t, pg, ns = int(t), int(pg), int(ns)
                 if pg:
                     ap += float(pg) * (float(t) / float(ns))
                 if t - pg < total_pos:
-                    d = abs(float(t) / float(total_pos) - recall_level)
                     idx = idx_before + int(e)
-                    if d < best[0] or (d == best[0] and idx > best[1]):
-                        best = (d, idx, int(ns - t))
+                    if t <= tstar:
+                        if idx > a[0]:
+                            a = (idx, t, ns - t)
+                    elif t < b[0] or (t == b[0] and idx > b[1]):
+                        b = (t, idx, ns - t)
             out.view(np.uint64)[0] = num
             out.view(np.float64)[1] = ap
-            out.view(np.float64)[2] = best[0]
-            out[3], out[4], out[5] = best[1], best[2], len(ends)
+            out[2], out[3], out[4] = a
+            out[5], out[6], out[7] = b
+            out[8] = len(ends)
         return torch.from_numpy(out)
 
     def empty_keys(self, n, tag):

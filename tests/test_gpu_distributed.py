@@ -1,0 +1,71 @@
+"""Pooled metric through the real CUDA ops + NCCL: world_size 1 always, world_size 2 when two GPUs are visible.
+Result must equal the single-segment GPU evaluation and the CPU oracle."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import dml_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _shard(rank, n=300_000):
+    rng = np.random.default_rng(7 + rank)
+    conf = rng.random(n).astype(np.float32)
+    conf[:n // 4] = np.round(conf[:n // 4] * 64) / 64
+    conf[rng.random(n) < 0.05] = 1.0
+    gt = rng.integers(0, 14, n).astype(np.uint8)
+    gt[rng.random(n) < 0.6] = 1
+    return conf, gt
+
+
+def _worker(rank, world, port, mode, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from dml_b200 import distributed as D
+        conf, gt = _shard(rank)
+        a, p, f, info = D.pooled_measures(torch.from_numpy(conf).cuda(), torch.from_numpy(gt).cuda(), (13,), mode=mode)
+        q.put((rank, a, p, f, info))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [1, 2])
+@pytest.mark.parametrize("mode", ["alltoall", "allgather"])
+def test_pooled_measures_nccl(world, mode):
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, mode, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = sorted(q.get(timeout=300) for _ in procs)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    shards = [_shard(r) for r in range(world)]
+    conf = np.concatenate([s[0] for s in shards])
+    gt = np.concatenate([s[1] for s in shards]).astype(np.int64)
+    ref = O.eval_ood_measure(conf, gt, (13,))
+    for r in results:
+        assert (r[1], r[2], r[3]) == (results[0][1], results[0][2], results[0][3])
+        np.testing.assert_allclose([r[1], r[2], r[3]], ref, rtol=0, atol=1e-12)
+        assert r[4]["n_groups"] == np.unique(conf).size

@@ -79,12 +79,23 @@ def test_host_helpers():
     assert head.scaled_identity_magnitude(torch.eye(13) * 3) == 3.0
     assert head.scaled_identity_magnitude(torch.ones(3, 3)) is None
     assert head.scaled_identity_magnitude(torch.eye(3)[:2]) is None
-    # combining range partials: sums, fixed-order float adds, argmin with "later index wins" ties
-    p0 = np.zeros(6, np.int64); p1 = np.zeros(6, np.int64)
-    p0.view(np.uint64)[0] = 10; p0.view(np.float64)[1] = 1.5; p0.view(np.float64)[2] = 0.05; p0[3] = 7; p0[4] = 3; p0[5] = 4
-    p1.view(np.uint64)[0] = 6; p1.view(np.float64)[1] = 0.5; p1.view(np.float64)[2] = 0.05; p1[3] = 9; p1[4] = 5; p1[5] = 2
-    a, p, f, g = ood.combine_partials([p0, p1], total_pos=4, total_n=12)
-    assert a == 16 / (2.0 * 4 * 8) and p == 2.0 / 4 and f == 5 / 8 and g == 6
+    # combining range partials: exact sums, two integer FPR candidates, float64 choice with "later group wins" ties
+    def part(num, ap, a, b, groups):
+        p = np.zeros(10, np.int64)
+        p.view(np.uint64)[0] = num
+        p.view(np.float64)[1] = ap
+        p[2:5] = a
+        p[5:8] = b
+        p[8] = groups
+        return p
+    none_b = (ood.NO_B, -1, 0)
+    p0 = part(10, 1.5, (7, 18, 3), none_b, 4)          # a: idx 7, tps 18 (recall 0.90), fps 3
+    p1 = part(6, 0.5, (-1, 0, 0), (20, 9, 5), 2)       # b: tps 20 (recall 1.00), idx 9, fps 5
+    a, p, f, g = ood.combine_partials([p0, p1], total_pos=20, total_n=28, recall_level=0.95)
+    assert a == 16 / (2.0 * 20 * 8) and p == 2.0 / 20 and g == 6
+    # |0.90-0.95| = 0.04999999999999993 < |1.00-0.95| = 0.050000000000000044 in float64 -> candidate a
+    assert f == 3 / 8
+    assert ood.combine_partials([p0, p1], 20, 28, recall_level=0.96)[2] == 5 / 8
     assert np.isnan(ood.combine_partials([p0], 0, 12)[0])
 
 
