@@ -11,6 +11,24 @@ __device__ __forceinline__ unsigned lanemask_lt() {
   return m;
 }
 
+// look-back words: gpu-scope relaxed accesses (served by L2), not the system-scope ones `volatile` emits
+__device__ __forceinline__ uint32_t ld_relaxed(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long ld_relaxed(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed(uint32_t* p, uint32_t v) {
+  asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void st_relaxed(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
 // Peer mask of the lanes holding the same 8-bit digit, built from 8 warp ballots (full-rate
 // VOTE + LOP3) instead of MATCH.ANY, which is far slower on sm_100.  Invalid lanes get an empty mask.
 __device__ __forceinline__ unsigned match_digit8(uint32_t d, bool valid) {
@@ -22,6 +40,28 @@ __device__ __forceinline__ unsigned match_digit8(uint32_t d, bool valid) {
     peers &= bit ? vote : ~vote;
   }
   return valid ? peers : 0u;
+}
+
+// Peer mask for one 8-bit digit in exactly 4 SASS instructions per bit (test bit -> predicate, VOTE,
+// predicated NOT, AND); nvcc's own code for the C++ form above spends 6.
+__device__ __forceinline__ unsigned match8_full(uint32_t d) {
+  unsigned peers;
+  asm volatile(
+      "{\n"
+      " .reg .pred p;\n"
+      " .reg .b32 v, t;\n"
+      " and.b32 t, %1, 1;   setp.ne.u32 p, t, 0; vote.sync.ballot.b32 %0, p, 0xffffffff; @!p not.b32 %0, %0;\n"
+      " and.b32 t, %1, 2;   setp.ne.u32 p, t, 0; vote.sync.ballot.b32 v, p, 0xffffffff; @!p not.b32 v, v; and.b32 %0, %0, v;\n"
+      " and.b32 t, %1, 4;   setp.ne.u32 p, t, 0; vote.sync.ballot.b32 v, p, 0xffffffff; @!p not.b32 v, v; and.b32 %0, %0, v;\n"
+      " and.b32 t, %1, 8;   setp.ne.u32 p, t, 0; vote.sync.ballot.b32 v, p, 0xffffffff; @!p not.b32 v, v; and.b32 %0, %0, v;\n"
+      " and.b32 t, %1, 16;  setp.ne.u32 p, t, 0; vote.sync.ballot.b32 v, p, 0xffffffff; @!p not.b32 v, v; and.b32 %0, %0, v;\n"
+      " and.b32 t, %1, 32;  setp.ne.u32 p, t, 0; vote.sync.ballot.b32 v, p, 0xffffffff; @!p not.b32 v, v; and.b32 %0, %0, v;\n"
+      " and.b32 t, %1, 64;  setp.ne.u32 p, t, 0; vote.sync.ballot.b32 v, p, 0xffffffff; @!p not.b32 v, v; and.b32 %0, %0, v;\n"
+      " and.b32 t, %1, 128; setp.ne.u32 p, t, 0; vote.sync.ballot.b32 v, p, 0xffffffff; @!p not.b32 v, v; and.b32 %0, %0, v;\n"
+      "}\n"
+      : "=r"(peers)
+      : "r"(d));
+  return peers;
 }
 
 // ---- digit histograms of every pass in one read of the keys --------------------------------
@@ -46,6 +86,7 @@ __global__ void __launch_bounds__(SORT_THREADS) hist_kernel(const uint32_t* __re
   const long long per_warp = chunk / SORT_WARPS;
   const long long wbeg = begin + (long long)w * per_warp;
   constexpr int U = 8;  // independent 128-byte warp loads in flight per step
+  const unsigned lt = lanemask_lt();
   for (long long off = 0; off < per_warp; off += 32 * U) {
     if (wbeg + off >= end) break;  // warp-uniform
     uint32_t key[U];
@@ -61,14 +102,16 @@ __global__ void __launch_bounds__(SORT_THREADS) hist_kernel(const uint32_t* __re
       for (int p = 0; p < MAX_PASSES; ++p) {
         if (p < n_passes) {
           const uint32_t d = (key[u] >> shifts[p]) & (RADIX - 1);
-          if (p < n_passes - 2) {
-            // low digit places are close to uniform: a warp-private shared atomic sees few same-address lanes
+          if (p < n_passes - 1) {
+            // lower digit places of float keys are close to uniform: a warp-private shared atomic sees few
+            // same-address lanes
             if (valid) atomicAdd(&s_h[w][p][d], 1u);
           } else {
-            // the top places of float keys are heavily skewed (a warp usually holds 1-3 distinct values):
-            // group equal digits with ballots, the group leader adds the group size (plain LDS/STS)
-            const unsigned peers = match_digit8(d, valid);
-            if (valid && lane == (__ffs(peers) - 1)) s_h[w][p][d] += (uint32_t)__popc(peers);
+            // the top place is heavily skewed (a warp usually holds 1-3 distinct values): group equal digits
+            // with ballots, the group's lowest lane adds the group size (plain LDS/STS)
+            const unsigned vm = __ballot_sync(0xffffffffu, valid);
+            const unsigned peers = match8_full(d) & vm;
+            if (valid && (peers & lt) == 0u) s_h[w][p][d] += (uint32_t)__popc(peers);
             __syncwarp();
           }
         }
@@ -117,28 +160,6 @@ struct LbTraits<unsigned long long> {
   static constexpr int FLAG_SHIFT = 62;
 };
 
-// Peer mask for one 8-bit digit in exactly 4 SASS instructions per bit (test bit -> predicate, VOTE,
-// predicated NOT, AND); nvcc's own code for the C++ form above spends 6.
-__device__ __forceinline__ unsigned match8_full(uint32_t d) {
-  unsigned peers;
-  asm volatile(
-      "{\n"
-      " .reg .pred p;\n"
-      " .reg .b32 v, t;\n"
-      " and.b32 t, %1, 1;   setp.ne.u32 p, t, 0; vote.sync.ballot.b32 %0, p, 0xffffffff; @!p not.b32 %0, %0;\n"
-      " and.b32 t, %1, 2;   setp.ne.u32 p, t, 0; vote.sync.ballot.b32 v, p, 0xffffffff; @!p not.b32 v, v; and.b32 %0, %0, v;\n"
-      " and.b32 t, %1, 4;   setp.ne.u32 p, t, 0; vote.sync.ballot.b32 v, p, 0xffffffff; @!p not.b32 v, v; and.b32 %0, %0, v;\n"
-      " and.b32 t, %1, 8;   setp.ne.u32 p, t, 0; vote.sync.ballot.b32 v, p, 0xffffffff; @!p not.b32 v, v; and.b32 %0, %0, v;\n"
-      " and.b32 t, %1, 16;  setp.ne.u32 p, t, 0; vote.sync.ballot.b32 v, p, 0xffffffff; @!p not.b32 v, v; and.b32 %0, %0, v;\n"
-      " and.b32 t, %1, 32;  setp.ne.u32 p, t, 0; vote.sync.ballot.b32 v, p, 0xffffffff; @!p not.b32 v, v; and.b32 %0, %0, v;\n"
-      " and.b32 t, %1, 64;  setp.ne.u32 p, t, 0; vote.sync.ballot.b32 v, p, 0xffffffff; @!p not.b32 v, v; and.b32 %0, %0, v;\n"
-      " and.b32 t, %1, 128; setp.ne.u32 p, t, 0; vote.sync.ballot.b32 v, p, 0xffffffff; @!p not.b32 v, v; and.b32 %0, %0, v;\n"
-      "}\n"
-      : "=r"(peers)
-      : "r"(d));
-  return peers;
-}
-
 // byte `sel` (0..3) of k: the digit when the shift is a multiple of 8 (PRMT, one instruction)
 __device__ __forceinline__ uint32_t digit_of(uint32_t k, int shift, uint32_t prmt_sel) {
   (void)shift;
@@ -147,7 +168,7 @@ __device__ __forceinline__ uint32_t digit_of(uint32_t k, int shift, uint32_t prm
 
 template <typename LB>
 __global__ void __launch_bounds__(SORT_THREADS, 3) onesweep_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out,
-                                                                   long long seg_len, int tiles_per_seg, int shift, int pass,
+                                                                   long long seg_len, int n_seg, int tiles_per_seg, int shift, int pass,
                                                                    const uint32_t* __restrict__ ghist_excl, LB* lookback,
                                                                    uint32_t* tickets) {
   using T = LbTraits<LB>;
@@ -155,13 +176,18 @@ __global__ void __launch_bounds__(SORT_THREADS, 3) onesweep_kernel(const uint32_
   __shared__ uint32_t s_keys[SORT_TILE];
   __shared__ uint32_t s_gbase[RADIX];   // global index of the tile's first key of each digit, minus its tile position
   __shared__ uint32_t s_scan[SORT_WARPS];
+  __shared__ uint32_t s_thist[RADIX];   // tile digit counts, published before the (serial) ranking phase
   __shared__ int s_tile;
 
   const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
-  const int seg = blockIdx.y;
+  // 1-D grid, blocks dealt round-robin to the segments: co-resident tiles come from many segments, which
+  // keeps every segment's look-back chain short
+  const int seg = (int)(blockIdx.x % (unsigned)n_seg);
   if (tid == 0) s_tile = (int)atomicAdd(tickets + seg, 1u);
+  const uint32_t gh = ghist_excl[((size_t)seg * MAX_PASSES + pass) * RADIX + tid];  // prefetch: used after the look-back
 #pragma unroll
   for (int i = 0; i < SORT_WARPS; ++i) s_whist[i][tid] = 0u;
+  s_thist[tid] = 0u;
   __syncthreads();
   const int tile = s_tile;
   const size_t seg_base = (size_t)seg * (size_t)seg_len;
@@ -193,9 +219,19 @@ __global__ void __launch_bounds__(SORT_THREADS, 3) onesweep_kernel(const uint32_
       peers[i] = valid ? (pm & vm) : 0u;
     }
   }
+  // ---- tile digit counts first (no serial dependency: one shared atomic per digit group), so that the
+  //      tile's LOCAL look-back entry is visible to its successors while this tile is still ranking --------
+  const unsigned lt = lanemask_lt();
+#pragma unroll
+  for (int i = 0; i < SORT_ITEMS; ++i)
+    if (peers[i] != 0u && (peers[i] & lt) == 0u) atomicAdd(&s_thist[digit_of(key[i], shift, sel)], (uint32_t)__popc(peers[i]));
+  __syncthreads();
+  const uint32_t run = s_thist[tid];
+  LB* lb = lookback + ((size_t)seg * tiles_per_seg + tile) * RADIX;
+  st_relaxed(lb + tid, (LB)((LB)run | (tile == 0 ? T::INCL : T::LOCAL)));
+
   // ---- rank within warp: every member reads the warp-private running count of its digit, the group's
   //      lowest lane advances it by the group size ------------------------------------------------
-  const unsigned lt = lanemask_lt();
   uint32_t* myhist = s_whist[w];
 #pragma unroll
   for (int i = 0; i < SORT_ITEMS; ++i) {
@@ -209,16 +245,16 @@ __global__ void __launch_bounds__(SORT_THREADS, 3) onesweep_kernel(const uint32_
   }
   __syncthreads();
 
-  // ---- thread t owns digit t: prefix over warps, publish, look back ----------------------------
-  uint32_t run = 0;
+  // ---- thread t owns digit t: prefix over warps, look back ----------------------------------------
+  {
+    uint32_t acc = 0;
 #pragma unroll
-  for (int ww = 0; ww < SORT_WARPS; ++ww) {
-    const uint32_t c = s_whist[ww][tid];
-    s_whist[ww][tid] = run;
-    run += c;
+    for (int ww = 0; ww < SORT_WARPS; ++ww) {
+      const uint32_t c = s_whist[ww][tid];
+      s_whist[ww][tid] = acc;
+      acc += c;
+    }
   }
-  volatile LB* lb = lookback + ((size_t)seg * tiles_per_seg + tile) * RADIX;
-  lb[tid] = (LB)run | (tile == 0 ? T::INCL : T::LOCAL);
 
   // exclusive scan of the tile's digit counts
   uint32_t incl = run;
@@ -234,21 +270,33 @@ __global__ void __launch_bounds__(SORT_THREADS, 3) onesweep_kernel(const uint32_
   for (int i = 0; i < SORT_WARPS; ++i)
     if (i < w) dbase += s_scan[i];
 
+  // Decoupled look-back with a window: LB_WIN predecessor entries are requested together (independent
+  // L2 round trips overlap), then consumed nearest-first until an INCLUSIVE entry closes the prefix.
   unsigned long long excl = 0;
   if (tile > 0) {
+    constexpr int LB_WIN = 8;
+    const LB* base = lookback + (size_t)seg * tiles_per_seg * RADIX + tid;
     int p = tile - 1;
-    while (true) {
-      volatile LB* q = lookback + ((size_t)seg * tiles_per_seg + p) * RADIX;
-      LB v;
-      do { v = q[tid]; } while ((v >> T::FLAG_SHIFT) == 0);
-      excl += (unsigned long long)(v & T::MASK);
-      if ((v >> T::FLAG_SHIFT) == 2) break;
-      --p;
+    bool done = false;
+    while (!done) {
+      LB v[LB_WIN];
+#pragma unroll
+      for (int j = 0; j < LB_WIN; ++j) v[j] = (p - j >= 0) ? ld_relaxed(base + (size_t)(p - j) * RADIX) : (LB)T::INCL;
+#pragma unroll
+      for (int j = 0; j < LB_WIN; ++j) {
+        if (!done) {
+          const unsigned flag = (unsigned)(v[j] >> T::FLAG_SHIFT);
+          if (flag == 0) break;            // not published yet: re-poll from this predecessor
+          excl += (unsigned long long)(v[j] & T::MASK);
+          --p;
+          if (flag == 2) done = true;
+        }
+      }
     }
-    lb[tid] = (LB)(excl + run) | T::INCL;
+    st_relaxed(lb + tid, (LB)((LB)(excl + run) | T::INCL));
   }
   // segment-relative index (seg_len < 2^32): wraps correctly in 32-bit arithmetic
-  s_gbase[tid] = ghist_excl[((size_t)seg * MAX_PASSES + pass) * RADIX + tid] + (uint32_t)excl - dbase;
+  s_gbase[tid] = gh + (uint32_t)excl - dbase;
 #pragma unroll
   for (int ww = 0; ww < SORT_WARPS; ++ww) s_whist[ww][tid] += dbase;
   __syncthreads();
@@ -319,14 +367,14 @@ int radix_sort_segments(uint32_t* keys, const SortPlan& plan, void* workspace, u
   }
   uint32_t* in = keys;
   uint32_t* out = alt;
-  dim3 grid((unsigned)plan.tiles_per_seg, (unsigned)plan.n_seg);
+  const unsigned grid = (unsigned)((size_t)plan.tiles_per_seg * plan.n_seg);
   for (int p = 0; p < plan.n_passes; ++p) {
     DML_CUDA_TRY(cudaMemsetAsync(lookback, 0, plan.off_end - plan.off_lookback, stream));  // look-back + tickets
     if (wide)
       onesweep_kernel<unsigned long long><<<grid, SORT_THREADS, 0, stream>>>(
-          in, out, plan.seg_len, plan.tiles_per_seg, plan.shifts[p], p, ghist, (unsigned long long*)lookback, tickets);
+          in, out, plan.seg_len, plan.n_seg, plan.tiles_per_seg, plan.shifts[p], p, ghist, (unsigned long long*)lookback, tickets);
     else
-      onesweep_kernel<uint32_t><<<grid, SORT_THREADS, 0, stream>>>(in, out, plan.seg_len, plan.tiles_per_seg,
+      onesweep_kernel<uint32_t><<<grid, SORT_THREADS, 0, stream>>>(in, out, plan.seg_len, plan.n_seg, plan.tiles_per_seg,
                                                                   plan.shifts[p], p, ghist, (uint32_t*)lookback, tickets);
     DML_LAUNCH_CHECK();
     uint32_t* t = in; in = out; out = t;
