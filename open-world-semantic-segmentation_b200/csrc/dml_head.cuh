@@ -45,7 +45,12 @@ struct HeadArgs {
   int crow, ccol;
   int B, K;
   long long HW;
+  unsigned out_mask;  // OUT_* bits: which outputs are wanted (hoists the pointer tests out of the kernel)
 };
+
+enum : unsigned { OUT_LABEL_U8 = 1u, OUT_LABEL_I64 = 2u, OUT_MAXLOGIT = 4u, OUT_EDS = 8u, OUT_MSP = 16u, OUT_MINMAX = 32u,
+                  OUT_CONF = 64u, OUT_GT_U8 = 128u, OUT_LOGITS = 256u, OUT_FEAT = 512u, OUT_NOVEL_DIST = 1024u };
+constexpr int HEAD_TILES_PER_BLOCK = 4;  // consecutive tiles of one image per CTA: block-level work is amortised
 
 // -(sum_d (x_d - mu_d)^2) in float64, in NumPy's pairwise-summation order for a contiguous
 // row of D elements (DeepLabV3Plus-Pytorch/test_embedding.py:430 is np.sum(..., axis=1) on a
@@ -139,24 +144,32 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_kernel(const HeadArgs a) {
   if ((EXTRA && n_novel > 0) || DENSE || nbins > 0) __syncthreads();
 
   const int b = blockIdx.y;
-  const long long p0 = ((long long)blockIdx.x * HEAD_THREADS + threadIdx.x) * VEC;
-  const bool active = p0 < a.HW;
   const uint64_t pol = policy_evict_first();
   const bool skip0 = a.first != 0;
-  const bool want_msp = (a.msp != nullptr) || a.want_msp_mm;
+  const unsigned om = a.out_mask;
+  const bool want_msp = (om & OUT_MSP) || a.want_msp_mm;
+  const float* x_img = a.x + ((long long)b * D) * a.HW;
+  // running per-thread min / max of the score maps (int order == float order for values >= 0)
+  int emin = 0x7fffffff, emax = (int)0x80000000, mmin = 0x7fffffff, mmax = (int)0x80000000;
+
+#pragma unroll 1
+  for (int it = 0; it < HEAD_TILES_PER_BLOCK; ++it) {
+  const long long p0 = (((long long)blockIdx.x * HEAD_TILES_PER_BLOCK + it) * HEAD_THREADS + threadIdx.x) * VEC;
+  const bool active = p0 < a.HW;
 
   float x[D][VEC];
   {
-    const float* xb = a.x + ((long long)b * D) * a.HW + p0;
+    const float* q = x_img + p0;
 #pragma unroll
     for (int d = 0; d < D; ++d) {
       FVec<VEC> t;
       if (active) {
-        t = ld_stream<VEC>(xb + (long long)d * a.HW, pol);
+        t = ld_stream<VEC>(q, pol);
       } else {
 #pragma unroll
         for (int v = 0; v < VEC; ++v) t.v[v] = 0.f;
       }
+      q += a.HW;
 #pragma unroll
       for (int v = 0; v < VEC; ++v) x[d][v] = t.v[v];
     }
@@ -168,7 +181,7 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_kernel(const HeadArgs a) {
 #pragma unroll
   for (int v = 0; v < VEC; ++v) { d0[v] = 0.f; dmin1[v] = PINF; esum1[v] = 0.f; ssum[v] = 0.f; arg1[v] = 0; }
   float* lg = nullptr;
-  if constexpr (EXTRA && !LOGITS) lg = a.logits ? a.logits + ((long long)b * K) * a.HW + p0 : nullptr;
+  if constexpr (EXTRA && !LOGITS) lg = (om & OUT_LOGITS) ? a.logits + ((long long)b * K) * a.HW + p0 : nullptr;
 
   auto visit = [&](int k, int v, float dk) {
     if (k == 0) {
@@ -335,7 +348,7 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_kernel(const HeadArgs a) {
         const double zn = novel_neg_dist<D, VEC>(x, v, s_novel + j * D);
         const double zmax = (double)(-dbest[v]);
         if (zn > a.novel_thr && zn > zmax) label[v] = a.novel_base + j;
-        if (a.novel_dist && active)
+        if ((om & OUT_NOVEL_DIST) && active)
           a.novel_dist[((long long)j * a.B + b) * a.HW + p0 + v] = zn;
       }
     }
@@ -343,7 +356,7 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_kernel(const HeadArgs a) {
 
   const long long pix = (long long)b * a.HW + p0;
   if (active) {
-    if (a.label_u8) {
+    if (om & OUT_LABEL_U8) {
       if constexpr (VEC == 4) {
         *reinterpret_cast<uchar4*>(a.label_u8 + pix) =
             make_uchar4((unsigned char)label[0], (unsigned char)label[1], (unsigned char)label[2], (unsigned char)label[3]);
@@ -353,7 +366,7 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_kernel(const HeadArgs a) {
         a.label_u8[pix] = (unsigned char)label[0];
       }
     }
-    if (a.label_i64) {
+    if (om & OUT_LABEL_I64) {
 #pragma unroll
       for (int v = 0; v < VEC; v += 2) {
         if constexpr (VEC >= 2) {
@@ -363,25 +376,25 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_kernel(const HeadArgs a) {
         }
       }
     }
-    if (a.maxlogit) {
+    if (om & OUT_MAXLOGIT) {
       FVec<VEC> t;
 #pragma unroll
       for (int v = 0; v < VEC; ++v) t.v[v] = -smin[v];
       st_keep<VEC>(a.maxlogit + pix, t);
     }
-    if (a.eds) {
+    if (om & OUT_EDS) {
       FVec<VEC> t;
 #pragma unroll
       for (int v = 0; v < VEC; ++v) t.v[v] = eds[v];
       st_keep<VEC>(a.eds + pix, t);
     }
-    if (a.msp) {
+    if (om & OUT_MSP) {
       FVec<VEC> t;
 #pragma unroll
       for (int v = 0; v < VEC; ++v) t.v[v] = mspv[v];
       st_keep<VEC>(a.msp + pix, t);
     }
-    if constexpr (EXTRA) if (a.feat) {
+    if constexpr (EXTRA) if (om & OUT_FEAT) {
       float* f = a.feat + pix * D;
 #pragma unroll
       for (int v = 0; v < VEC; ++v)
@@ -390,42 +403,23 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_kernel(const HeadArgs a) {
     }
   }
 
-  // ---- per-image min / max of the raw score maps (for the min-max normalisation) ---------
-  if (a.minmax && (a.want_eds_mm || a.want_msp_mm)) {
-    int emin = 0x7fffffff, emax = (int)0x80000000, mmin = 0x7fffffff, mmax = (int)0x80000000;
-    if (active) {
+  // ---- running min / max of the raw score maps (reduced per block after the tile loop) ----------
+  if ((om & OUT_MINMAX) && active) {
 #pragma unroll
-      for (int v = 0; v < VEC; ++v) {
-        const int e = __float_as_int(eds[v]), m = __float_as_int(mspv[v]);
-        emin = min(emin, e); emax = max(emax, e);
-        mmin = min(mmin, m); mmax = max(mmax, m);
-      }
-    }
-    emin = __reduce_min_sync(0xffffffffu, emin); emax = __reduce_max_sync(0xffffffffu, emax);
-    mmin = __reduce_min_sync(0xffffffffu, mmin); mmax = __reduce_max_sync(0xffffffffu, mmax);
-    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-    if (l == 0) { s_red[0][w] = emin; s_red[1][w] = emax; s_red[2][w] = mmin; s_red[3][w] = mmax; }
-    __syncthreads();
-    if (threadIdx.x < 4) {
-      int r = s_red[threadIdx.x][0];
-      const bool is_min = (threadIdx.x & 1) == 0;
-#pragma unroll
-      for (int i = 1; i < HEAD_THREADS / 32; ++i) r = is_min ? min(r, s_red[threadIdx.x][i]) : max(r, s_red[threadIdx.x][i]);
-      const bool wanted = threadIdx.x < 2 ? a.want_eds_mm : a.want_msp_mm;
-      if (wanted) {
-        int* dst = a.minmax + b * 4 + threadIdx.x;
-        if (is_min) atomicMin(dst, r); else atomicMax(dst, r);
-      }
+    for (int v = 0; v < VEC; ++v) {
+      const int e = __float_as_int(eds[v]), m = __float_as_int(mspv[v]);
+      emin = min(emin, e); emax = max(emax, e);
+      mmin = min(mmin, m); mmax = max(mmax, m);
     }
   }
 
-  // ---- fused confusion counts -------------------------------------------------------------
-  if (nbins > 0) {
+  // ---- fused confusion counts (block-shared histogram, flushed once after the tile loop) -----------
+  if (om & OUT_CONF) {
     int bin[VEC];
 #pragma unroll
     for (int v = 0; v < VEC; ++v) bin[v] = -1;
     if (active) {
-      if (a.gt_u8) {
+      if (om & OUT_GT_U8) {
         unsigned char g[VEC];
         if constexpr (VEC == 4) {
           const uchar4 t = *reinterpret_cast<const uchar4*>(a.gt_u8 + pix);
@@ -449,6 +443,28 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_kernel(const HeadArgs a) {
     }
 #pragma unroll
     for (int v = 0; v < VEC; ++v) warp_histogram_add(s_conf, bin[v]);
+  }
+  }  // tile loop
+
+  if (om & OUT_MINMAX) {
+    emin = __reduce_min_sync(0xffffffffu, emin); emax = __reduce_max_sync(0xffffffffu, emax);
+    mmin = __reduce_min_sync(0xffffffffu, mmin); mmax = __reduce_max_sync(0xffffffffu, mmax);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) { s_red[0][w] = emin; s_red[1][w] = emax; s_red[2][w] = mmin; s_red[3][w] = mmax; }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+      int r = s_red[threadIdx.x][0];
+      const bool is_min = (threadIdx.x & 1) == 0;
+#pragma unroll
+      for (int i = 1; i < HEAD_THREADS / 32; ++i) r = is_min ? min(r, s_red[threadIdx.x][i]) : max(r, s_red[threadIdx.x][i]);
+      const bool wanted = threadIdx.x < 2 ? a.want_eds_mm : a.want_msp_mm;
+      if (wanted) {
+        int* dst = a.minmax + b * 4 + threadIdx.x;
+        if (is_min) atomicMin(dst, r); else atomicMax(dst, r);
+      }
+    }
+  }
+  if (om & OUT_CONF) {
     __syncthreads();
     for (int i = threadIdx.x; i < nbins; i += HEAD_THREADS) {
       const unsigned c = s_conf[i];
@@ -460,7 +476,7 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_kernel(const HeadArgs a) {
 template <int D, int MODE, int VEC, bool EXTRA>
 int launch_head(const HeadArgs& a, cudaStream_t stream) {
   constexpr int DP = (D + 3) & ~3;
-  const long long per_block = (long long)HEAD_THREADS * VEC;
+  const long long per_block = (long long)HEAD_THREADS * VEC * HEAD_TILES_PER_BLOCK;
   dim3 grid((unsigned)((a.HW + per_block - 1) / per_block), (unsigned)a.B);
   size_t smem = (EXTRA ? (size_t)a.n_novel * D * sizeof(double) : 0) + (MODE == HEAD_DENSE ? (size_t)a.K * DP * sizeof(float) : 0) +
                 (a.conf ? (size_t)a.crow * a.ccol * sizeof(unsigned) : 0);
