@@ -392,7 +392,7 @@ __global__ void __launch_bounds__(CARRY_THREADS) scan_carry_kernel(const Agg* __
 }
 
 // phase 3: per-tile group contributions
-__global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(const uint32_t* __restrict__ keys, long long seg_len,
+__global__ void __launch_bounds__(SCAN_THREADS, 3) scan_apply_kernel(const uint32_t* __restrict__ keys, long long seg_len,
                                                                   int tiles_per_seg, const Carry* __restrict__ tile_carry,
                                                                   const RangeInfo* __restrict__ info, double recall_level,
                                                                   TilePartial* __restrict__ partials) {
@@ -425,27 +425,38 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(const uint32_t
   for (int i = 0; i < w; ++i) wpre = agg_combine(wpre, s_w[i]);
   excl = agg_combine(wpre, excl);
 
+  // Everything inside the tile is 32-bit and relative to this thread's first element; 64-bit values are
+  // formed once per thread (and at the rare group ends that carry an open group in from earlier tiles).
   const Carry tc = tile_carry[(size_t)seg * tiles_per_seg + tile];
-  long long P = (long long)(tc.pos + excl.pos);                       // positives ranked so far (inclusive)
-  long long spos = (long long)(excl.head ? excl.spos : tc.spos + excl.spos);
-  long long slen = (long long)(excl.head ? excl.slen : tc.slen + excl.slen);
+  const long long base_P = (long long)(tc.pos + excl.pos);                      // positives ranked before my run
+  const long long open_pos = (long long)(excl.head ? excl.spos : tc.spos + excl.spos);   // open group before my run
+  const long long open_len = (long long)(excl.head ? excl.slen : tc.slen + excl.slen);
   const long long Ptot = ri.total_pos;
+  const long long first_idx = ri.idx_before + first;
+  // thresholds in local terms, clamped to [-1, SCAN_ITEMS + 1]
+  auto clamp_local = [](long long v) { return (int)(v < -1 ? -1 : (v > SCAN_ITEMS + 1 ? SCAN_ITEMS + 1 : v)); };
+  const int t_local = clamp_local(tstar - base_P);            // tps <= T*        <=>  Pl <= t_local
+  const int rem_local = clamp_local(Ptot - base_P);           // tps_{g-1} < Ptot <=>  Pl_start < rem_local
+  const bool open_valid = (base_P - open_pos) < Ptot;         // same test for the group carried in
 
   TilePartial acc;
   partial_init(acc);
+  unsigned long long neg_P = 0ull, tie = 0ull;   // sum over negatives of Pl ; sum over mixed groups of neg_g * pos_g
+  int n_neg = 0;
+  int Pl = 0, ls = 0, ll = 0, Pl_start = 0;
+  bool in_thread = false;                        // current group started inside my run
+  int a_j = -1, a_Pl = 0, b_j = -1, b_Pl = 0, ngroups = 0;
 
-  uint32_t prev = tk.prev;
-  bool have_prev = tk.has_prev;
+  bool head = !tk.has_prev || ((tk.k[0] >> 1) != (tk.prev >> 1));
 #pragma unroll
   for (int j = 0; j < SCAN_ITEMS; ++j) {
     const long long gi = first + j;
     if (gi < seg_len) {
       const uint32_t key = tk.k[j];
-      const bool head = !have_prev || ((key >> 1) != (prev >> 1));
-      const long long p = (long long)(key & 1u);
-      if (head) { spos = 0; slen = 0; }
-      P += p; spos += p; slen += 1;
-      prev = key; have_prev = true;
+      const int p = (int)(key & 1u);
+      if (head) { ls = 0; ll = 0; Pl_start = Pl; in_thread = true; }
+      if (!p) { neg_P += (unsigned)Pl; ++n_neg; }
+      Pl += p; ls += p; ll += 1;
       // group end: the next element (if any) opens a new group
       bool endg;
       if (gi + 1 >= seg_len) endg = true;
@@ -454,38 +465,54 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(const uint32_t
         endg = (nk >> 1) != (key >> 1);
       }
       if (endg) {
-        const long long idx = ri.idx_before + gi;
-        const long long n_so_far = idx + 1;
-        const long long fps = n_so_far - P;
-        acc.auroc_num += (unsigned long long)((slen - spos) * (2 * P - spos));
-        if (spos) acc.ap_sum += (double)spos * ((double)P / (double)n_so_far);   // rare: positives are few
-        if (P - spos < Ptot) {                                               // groups up to the first with full recall
-          if (P <= tstar) {
-            if (idx > acc.a_idx) { acc.a_idx = idx; acc.a_tps = P; acc.a_fps = fps; }
-          } else if (P < acc.b_tps || (P == acc.b_tps && idx > acc.b_idx)) {
-            acc.b_tps = P; acc.b_idx = idx; acc.b_fps = fps;
-          }
+        const long long pos_g = in_thread ? (long long)ls : open_pos + ls;
+        const long long len_g = in_thread ? (long long)ll : open_len + ll;
+        if (pos_g) {
+          const long long neg_g = len_g - pos_g;
+          if (neg_g) tie += (unsigned long long)(neg_g * pos_g);
+          acc.ap_sum += (double)pos_g * ((double)(base_P + Pl) / (double)(first_idx + j + 1));
         }
-        ++acc.n_groups;
+        const bool valid = in_thread ? (Pl_start < rem_local) : open_valid;   // groups up to the first with full recall
+        if (valid) {
+          if (Pl <= t_local) { a_j = j; a_Pl = Pl; }
+          else if (b_j < 0 || Pl == b_Pl) { b_j = j; b_Pl = Pl; }
+        }
+        ++ngroups;
       }
+      head = endg;
     }
   }
-  // block reduction (fixed order)
+  // ---- block reduction.  Sums: fixed-order shuffles.  FPR candidates: the winning thread is found with one
+  //      32-bit warp reduction on a tile-local key, only the winner materialises the 64-bit tuple. ----------
+  unsigned long long auroc = 2ull * ((unsigned long long)n_neg * (unsigned long long)base_P + neg_P) + tie;
+  double ap = acc.ap_sum;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
-    TilePartial other;
-    other.auroc_num = __shfl_down_sync(0xffffffffu, acc.auroc_num, o);
-    other.ap_sum = __shfl_down_sync(0xffffffffu, acc.ap_sum, o);
-    other.a_idx = __shfl_down_sync(0xffffffffu, acc.a_idx, o);
-    other.a_tps = __shfl_down_sync(0xffffffffu, acc.a_tps, o);
-    other.a_fps = __shfl_down_sync(0xffffffffu, acc.a_fps, o);
-    other.b_tps = __shfl_down_sync(0xffffffffu, acc.b_tps, o);
-    other.b_idx = __shfl_down_sync(0xffffffffu, acc.b_idx, o);
-    other.b_fps = __shfl_down_sync(0xffffffffu, acc.b_fps, o);
-    other.n_groups = __shfl_down_sync(0xffffffffu, acc.n_groups, o);
-    partial_merge(acc, other);
+    auroc += __shfl_down_sync(0xffffffffu, auroc, o);
+    ap += __shfl_down_sync(0xffffffffu, ap, o);
   }
-  if (lane == 0) s_p[w] = acc;
+  const int ng_w = __reduce_add_sync(0xffffffffu, ngroups);
+  // a: the latest group end with tps <= T*  -> max tile-local element index
+  const int a_key = a_j >= 0 ? tid * SCAN_ITEMS + a_j : -1;
+  const int a_best = __reduce_max_sync(0xffffffffu, a_key);
+  // b: smallest tps > T*, then the latest index.  tps grows with the index, so order by the positives counted
+  //    inside the tile (excl.pos + Pl <= SCAN_TILE) and, among equals, by the reversed index.
+  const unsigned b_key = b_j >= 0 ? (((unsigned)(excl.pos + (unsigned)b_Pl)) << 13) | (unsigned)(SCAN_TILE - 1 - (tid * SCAN_ITEMS + b_j))
+                                  : 0xffffffffu;
+  const unsigned b_best = __reduce_min_sync(0xffffffffu, b_key);
+  if (lane == 0) {
+    TilePartial t;
+    partial_init(t);
+    t.auroc_num = auroc; t.ap_sum = ap; t.n_groups = ng_w;
+    s_p[w] = t;
+  }
+  __syncwarp();
+  if (a_j >= 0 && a_key == a_best) {
+    s_p[w].a_idx = first_idx + a_j; s_p[w].a_tps = base_P + a_Pl; s_p[w].a_fps = first_idx + a_j + 1 - (base_P + a_Pl);
+  }
+  if (b_j >= 0 && b_key == b_best) {
+    s_p[w].b_idx = first_idx + b_j; s_p[w].b_tps = base_P + b_Pl; s_p[w].b_fps = first_idx + b_j + 1 - (base_P + b_Pl);
+  }
   __syncthreads();
   if (tid == 0) {
     TilePartial t = s_p[0];

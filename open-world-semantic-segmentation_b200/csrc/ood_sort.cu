@@ -167,7 +167,7 @@ __device__ __forceinline__ uint32_t digit_of(uint32_t k, int shift, uint32_t prm
 }
 
 template <typename LB>
-__global__ void __launch_bounds__(SORT_THREADS, 3) onesweep_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out,
+__global__ void __launch_bounds__(SORT_THREADS, 4) onesweep_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out,
                                                                    long long seg_len, int n_seg, int tiles_per_seg, int shift, int pass,
                                                                    const uint32_t* __restrict__ ghist_excl, LB* lookback,
                                                                    uint32_t* tickets) {
@@ -176,7 +176,6 @@ __global__ void __launch_bounds__(SORT_THREADS, 3) onesweep_kernel(const uint32_
   __shared__ uint32_t s_keys[SORT_TILE];
   __shared__ uint32_t s_gbase[RADIX];   // global index of the tile's first key of each digit, minus its tile position
   __shared__ uint32_t s_scan[SORT_WARPS];
-  __shared__ uint32_t s_thist[RADIX];   // tile digit counts, published before the (serial) ranking phase
   __shared__ int s_tile;
 
   const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
@@ -187,7 +186,6 @@ __global__ void __launch_bounds__(SORT_THREADS, 3) onesweep_kernel(const uint32_
   const uint32_t gh = ghist_excl[((size_t)seg * MAX_PASSES + pass) * RADIX + tid];  // prefetch: used after the look-back
 #pragma unroll
   for (int i = 0; i < SORT_WARPS; ++i) s_whist[i][tid] = 0u;
-  s_thist[tid] = 0u;
   __syncthreads();
   const int tile = s_tile;
   const size_t seg_base = (size_t)seg * (size_t)seg_len;
@@ -199,7 +197,6 @@ __global__ void __launch_bounds__(SORT_THREADS, 3) onesweep_kernel(const uint32_
 
   // ---- load (warp-striped inside the warp's contiguous slice => LSD-stable order) ----------
   uint32_t key[SORT_ITEMS];
-  uint32_t rank[SORT_ITEMS];
   unsigned peers[SORT_ITEMS];
   const int wbase = w * 32 * SORT_ITEMS;
   const uint32_t* src = in + seg_base + tile_off + wbase + lane;
@@ -219,44 +216,27 @@ __global__ void __launch_bounds__(SORT_THREADS, 3) onesweep_kernel(const uint32_
       peers[i] = valid ? (pm & vm) : 0u;
     }
   }
-  // ---- tile digit counts first (no serial dependency: one shared atomic per digit group), so that the
-  //      tile's LOCAL look-back entry is visible to its successors while this tile is still ranking --------
+  // ---- per-warp digit counts, order-free: the lowest lane of every digit group adds the group size to its
+  //      warp's row (shared atomic, no serial chain) ------------------------------------------------------
   const unsigned lt = lanemask_lt();
+  uint32_t* myhist = s_whist[w];
 #pragma unroll
   for (int i = 0; i < SORT_ITEMS; ++i)
-    if (peers[i] != 0u && (peers[i] & lt) == 0u) atomicAdd(&s_thist[digit_of(key[i], shift, sel)], (uint32_t)__popc(peers[i]));
+    if (peers[i] != 0u && (peers[i] & lt) == 0u) atomicAdd(&myhist[digit_of(key[i], shift, sel)], (uint32_t)__popc(peers[i]));
   __syncthreads();
-  const uint32_t run = s_thist[tid];
+
+  // ---- thread t owns digit t: prefix over warps -> tile count; publish the LOCAL look-back entry early ------
+  uint32_t run = 0;
+#pragma unroll
+  for (int ww = 0; ww < SORT_WARPS; ++ww) {
+    const uint32_t c = s_whist[ww][tid];
+    s_whist[ww][tid] = run;
+    run += c;
+  }
   LB* lb = lookback + ((size_t)seg * tiles_per_seg + tile) * RADIX;
   st_relaxed(lb + tid, (LB)((LB)run | (tile == 0 ? T::INCL : T::LOCAL)));
 
-  // ---- rank within warp: every member reads the warp-private running count of its digit, the group's
-  //      lowest lane advances it by the group size ------------------------------------------------
-  uint32_t* myhist = s_whist[w];
-#pragma unroll
-  for (int i = 0; i < SORT_ITEMS; ++i) {
-    const uint32_t d = digit_of(key[i], shift, sel);
-    const uint32_t below = (uint32_t)__popc(peers[i] & lt);
-    const uint32_t c = myhist[d];
-    __syncwarp();
-    if (below == 0 && peers[i] != 0) myhist[d] = c + (uint32_t)__popc(peers[i]);
-    __syncwarp();
-    rank[i] = c + below;
-  }
-  __syncthreads();
-
-  // ---- thread t owns digit t: prefix over warps, look back ----------------------------------------
-  {
-    uint32_t acc = 0;
-#pragma unroll
-    for (int ww = 0; ww < SORT_WARPS; ++ww) {
-      const uint32_t c = s_whist[ww][tid];
-      s_whist[ww][tid] = acc;
-      acc += c;
-    }
-  }
-
-  // exclusive scan of the tile's digit counts
+  // exclusive scan of the tile's digit counts -> start of every digit inside the sorted tile
   uint32_t incl = run;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
@@ -269,9 +249,27 @@ __global__ void __launch_bounds__(SORT_THREADS, 3) onesweep_kernel(const uint32_
 #pragma unroll
   for (int i = 0; i < SORT_WARPS; ++i)
     if (i < w) dbase += s_scan[i];
+#pragma unroll
+  for (int ww = 0; ww < SORT_WARPS; ++ww) s_whist[ww][tid] += dbase;   // running write position of (warp, digit)
+  __syncthreads();
 
-  // Decoupled look-back with a window: LB_WIN predecessor entries are requested together (independent
-  // L2 round trips overlap), then consumed nearest-first until an INCLUSIVE entry closes the prefix.
+  // ---- rank + local scatter in one sweep: every member reads the running position of its (warp, digit), the
+  //      group's lowest lane advances it by the group size; keys land in digit order in shared memory --------
+#pragma unroll
+  for (int i = 0; i < SORT_ITEMS; ++i) {
+    const uint32_t d = digit_of(key[i], shift, sel);
+    const uint32_t below = (uint32_t)__popc(peers[i] & lt);
+    const uint32_t c = myhist[d];
+    __syncwarp();
+    if (peers[i] != 0u) {
+      if (below == 0) myhist[d] = c + (uint32_t)__popc(peers[i]);
+      s_keys[c + below] = key[i];
+    }
+    __syncwarp();
+  }
+
+  // ---- decoupled look-back with a window: LB_WIN predecessor entries are requested together (independent
+  //      L2 round trips overlap), then consumed nearest-first until an INCLUSIVE entry closes the prefix ----
   unsigned long long excl = 0;
   if (tile > 0) {
     constexpr int LB_WIN = 8;
@@ -297,19 +295,9 @@ __global__ void __launch_bounds__(SORT_THREADS, 3) onesweep_kernel(const uint32_
   }
   // segment-relative index (seg_len < 2^32): wraps correctly in 32-bit arithmetic
   s_gbase[tid] = gh + (uint32_t)excl - dbase;
-#pragma unroll
-  for (int ww = 0; ww < SORT_WARPS; ++ww) s_whist[ww][tid] += dbase;
   __syncthreads();
 
-  // ---- local scatter into digit order, then coalesced runs to global -----------------------------
-#pragma unroll
-  for (int i = 0; i < SORT_ITEMS; ++i) {
-    if (full || (wbase + i * 32 + lane) < nvalid) {
-      const uint32_t d = digit_of(key[i], shift, sel);
-      s_keys[myhist[d] + rank[i]] = key[i];
-    }
-  }
-  __syncthreads();
+  // ---- coalesced per-digit runs to global -------------------------------------------------------------------
   uint32_t* dst = out + seg_base;
 #pragma unroll
   for (int j = 0; j < SORT_ITEMS; ++j) {
