@@ -118,6 +118,50 @@ typedef struct dml_head_params {
 
 DML_API int dml_head_forward(const dml_head_params* p, dml_stream_t stream);
 
+/* ------------------------------------------------------------------------------------ *
+ * (a2) Fused multi-scale bilinear upsample + average + score head (anomaly path).
+ *
+ * Replaces, without materialising any full-resolution [B,K,H,W] tensor:
+ *   anomaly/models/models.py:659-661         F.interpolate(z_s, segSize, 'bilinear', align_corners=False)
+ *   anomaly/eval_ood_traditional.py:192-208  scores = scores + scores_tmp / len(imgSizes), per scale in order
+ *   anomaly/eval_ood_traditional.py:212-218,276-305,434  (tmp_scores / argmax / msp / maxlogit / EDS as in
+ *                                             dml_head_forward with input_is_logits)
+ * z[s] are the stride-8 distance logits of scale s ([B,K,h[s],w[s]], e.g. dml_head_forward(logits=...) on
+ * the decoder's embedding); the kernel evaluates, per output pixel and class,
+ *   scores[k] = sum_s ( h0*(w0*z00 + w1*z01) + h1*(w0*z10 + w1*z11) ) / n_scales
+ * with torch's upsample_bilinear2d source-index / lambda arithmetic in fp32 and the accumulation order of
+ * the reference loop.  `reciprocal_average` == 0: correctly rounded division (torch CPU semantics);
+ * != 0: multiplication by fl(1/n_scales) (what torch's CUDA div-by-scalar kernel computes).
+ * `scores` (optional) receives the averaged full-resolution maps; with every score output NULL the call is
+ * the plain "upsample + average" of :209-210 (`ft1`, fed with the low-resolution embeddings).
+ * Remaining fields have the meaning they have in dml_head_params.
+ * ------------------------------------------------------------------------------------ */
+#define DML_MAX_SCALES 8
+typedef struct dml_multiscale_params {
+  uint32_t struct_bytes;      /* sizeof(dml_multiscale_params), ABI guard */
+  int32_t B, K, H, W;         /* output maps are [B,*,H,W] */
+  int32_t n_scales;           /* 1..DML_MAX_SCALES */
+  const float* z[DML_MAX_SCALES]; /* [B,K,h[s],w[s]] */
+  int32_t h[DML_MAX_SCALES], w[DML_MAX_SCALES];
+  int32_t reciprocal_average;
+  int32_t score_first_class;
+  float eds_clamp;
+  float* scores;              /* [B,K,H,W] or NULL */
+  uint8_t* label_u8;
+  int64_t* label_i64;
+  float* maxlogit;
+  float* eds;
+  float* msp;
+  float* minmax;              /* [B,4] */
+  int32_t want_eds_minmax, want_msp_minmax;
+  const uint8_t* gt_u8;
+  const int64_t* gt_i64;
+  unsigned long long* confusion;
+  int32_t conf_rows, conf_cols;
+} dml_multiscale_params;
+
+DML_API int dml_multiscale_head_forward(const dml_multiscale_params* p, dml_stream_t stream);
+
 /* Per-image min-max normalise + mix (anomaly/eval_ood_traditional.py:101-106,305,435,447-448):
  *   eds_n = (eds - min)/(max - min), msp_n likewise, c = 1/(1+exp(lambda (eds_n - thr))),
  *   mix = c*eds_n + (1-c)*msp_n.  In-place allowed (out == in).  Outputs may be NULL.

@@ -15,6 +15,7 @@ from ._lib import DmlError, load_library  # noqa: F401
 from . import head, ood  # noqa: F401
 from . import autograd, anomaly, deeplab, prototypes  # noqa: F401
 from .autograd import distance_logits, dml_loss  # noqa: F401
-from .head import HeadOutput, confusion_counts, dml_head, finalize_scores, plm_merge  # noqa: F401
+from .head import (HeadOutput, confusion_counts, dml_head, dml_multiscale_head, finalize_scores,  # noqa: F401
+                   multiscale_average, plm_merge)
 
 __version__ = "0.1.0"

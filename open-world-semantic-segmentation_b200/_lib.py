@@ -38,6 +38,25 @@ class HeadParams(C.Structure):
     ]
 
 
+MAX_SCALES = 8
+
+
+class MultiscaleParams(C.Structure):
+    """Mirror of ``dml_multiscale_params`` (include/dml_b200.h)."""
+    _fields_ = [
+        ("struct_bytes", C.c_uint32),
+        ("B", C.c_int32), ("K", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
+        ("n_scales", C.c_int32),
+        ("z", C.c_void_p * MAX_SCALES), ("h", C.c_int32 * MAX_SCALES), ("w", C.c_int32 * MAX_SCALES),
+        ("reciprocal_average", C.c_int32), ("score_first_class", C.c_int32), ("eds_clamp", C.c_float),
+        ("scores", C.c_void_p), ("label_u8", C.c_void_p), ("label_i64", C.c_void_p),
+        ("maxlogit", C.c_void_p), ("eds", C.c_void_p), ("msp", C.c_void_p), ("minmax", C.c_void_p),
+        ("want_eds_minmax", C.c_int32), ("want_msp_minmax", C.c_int32),
+        ("gt_u8", C.c_void_p), ("gt_i64", C.c_void_p), ("confusion", C.c_void_p),
+        ("conf_rows", C.c_int32), ("conf_cols", C.c_int32),
+    ]
+
+
 class OodResult(C.Structure):
     """Mirror of ``dml_ood_result``."""
     _fields_ = [("auroc", C.c_double), ("aupr", C.c_double), ("fpr", C.c_double),
@@ -55,6 +74,7 @@ SIGNATURES = {
     "dml_max_dim": (C.c_int, []),
     "dml_kernel_launches": (C.c_ulonglong, []),
     "dml_head_forward": (C.c_int, [C.POINTER(HeadParams), C.c_void_p]),
+    "dml_multiscale_head_forward": (C.c_int, [C.POINTER(MultiscaleParams), C.c_void_p]),
     "dml_scores_finalize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_float,
                                       C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "dml_confusion": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32,

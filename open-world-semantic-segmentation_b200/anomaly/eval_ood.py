@@ -46,6 +46,43 @@ def score_map(scores: torch.Tensor, mode: str = "dissum", exclude_back: bool = F
     return out.label, {"dissum": eds_n, "mmsp": msp_n, "mix": mix}[mode]
 
 
+def multiscale_scores(z_list, segSize, *, want_ft_from=None, reciprocal_average: bool = False):
+    """The multi-scale loop of ``evaluate()`` (anomaly/eval_ood_traditional.py:192-210) on stride-8 inputs:
+    ``scores = sum_s F.interpolate(z_s, segSize) / S`` (and ``ft1`` likewise from the low-resolution
+    embeddings ``want_ft_from``), each in ONE kernel that reads only the low-resolution maps.
+    Returns ``scores`` [B,K,H,W] or ``(scores, ft1)``."""
+    scores = H.multiscale_average(z_list, segSize, reciprocal_average=reciprocal_average)
+    if want_ft_from is None:
+        return scores
+    return scores, H.multiscale_average(want_ft_from, segSize, reciprocal_average=reciprocal_average)
+
+
+def multiscale_score_map(z_list, segSize, mode: str = "dissum", exclude_back: bool = False,
+                         clamp: float = H.CLAMP_ANOMALY, lam: float = 50.0, thr: float = 0.2,
+                         reciprocal_average: bool = False):
+    """``score_map(multiscale_scores(z_list, segSize), mode)`` without materialising ``scores``: the
+    upsample + average (:198-208) is fused into the score head (:212-305,434-450).
+    Returns (pred int64 [B,H,W], conf fp32 [B,H,W])."""
+    if mode not in OOD_MODES:
+        raise ValueError(f"unsupported OOD.ood '{mode}' (crf / knn are outside the DML hot path)")
+    if mode == "background":
+        scores = H.multiscale_average(z_list, segSize, reciprocal_average=reciprocal_average)
+        return score_map(scores, mode, exclude_back)
+    want_eds = mode in ("dissum", "mix")
+    want_msp = mode in ("msp", "mmsp", "mix")
+    out = H.dml_multiscale_head(z_list, segSize, reciprocal_average=reciprocal_average, label_dtype=torch.int64,
+                                want_maxlogit=(mode == "maxlogit"), want_eds=want_eds, eds_clamp=clamp,
+                                want_msp=want_msp, want_minmax=mode in ("dissum", "mmsp", "mix"),
+                                exclude_back=exclude_back)
+    if mode == "msp":
+        return out.label, out.msp
+    if mode == "maxlogit":
+        return out.label, out.maxlogit
+    eds_n, msp_n, mix = H.finalize_scores(out.eds, out.msp, out.minmax, want_eds=want_eds, want_msp=(mode == "mmsp"),
+                                          want_mix=(mode == "mix"), lam=lam, thr=thr)
+    return out.label, {"dissum": eds_n, "mmsp": msp_n, "mix": mix}[mode]
+
+
 def eval_ood_measure(conf, seg_label, cfg, mask=None):
     """anomaly/eval_ood_traditional.py:128-148 (``cfg.OOD.out_labels``; ``mask`` filters the labels
     only -- like the reference, ``conf`` must then already be masked)."""
@@ -110,6 +147,42 @@ class EmbeddingEvaluator:
         conf = None
         if self.store_conf:
             if self._conf is None or self._conf.shape != out.eds.shape or self._conf.device != x.device:
+                self._conf = torch.empty_like(out.eds)
+            conf = self._conf
+        res, stats = ood.eval_segments(out.eds, B, Hh * Ww, gt=gt, out_labels=self.out_labels, score_kind=0,
+                                       minmax=out.minmax, minmax_slot=0, conf_out=conf,
+                                       recall_level=self.recall_level, workspace=self._ws)
+        return BatchEval(out.label, conf, out.msp, out.confusion, res, stats)
+
+
+class MultiScaleEvaluator(EmbeddingEvaluator):
+    """The anomaly sub-project's real data flow (SURVEY.md section 8 rows a1 + a2): per scale the stride-8
+    embedding [B,K,h_s,w_s] of ``conv_last`` -> stride-8 distance logits (``dml_head_forward``, tiny) ->
+    ONE fused kernel that bilinearly upsamples every scale to ``segSize``, averages them in the reference's
+    order and emits labels, raw EDS / MSP, per-image min/max and confusion counts
+    (``dml_multiscale_head_forward``) -> key-gen with the normalisation folded in -> segmented sort -> scan.
+    HBM traffic per output pixel: ~10 B written (label, EDS, MSP) instead of the ~1 KB the reference moves
+    for its ten full-resolution interpolations and read-modify-write accumulations."""
+
+    def __call__(self, emb_list, gt: torch.Tensor, confusion: Optional[torch.Tensor] = None,
+                 inputs_are_logits: bool = False, reciprocal_average: bool = False) -> BatchEval:
+        B, Hh, Ww = gt.shape
+        dev = gt.device
+        if inputs_are_logits:
+            z_list = emb_list
+        else:
+            z_list = [H.dml_head(e, magnitude=self.magnitude, want_logits=True, label_dtype=None).logits for e in emb_list]
+        if self._out is not None and (self._out.label.shape != (B, Hh, Ww) or self._out.label.device != dev):
+            self._out = None
+        if self._ws is None or self._ws.device != dev:
+            self._ws = ood.OodWorkspace(dev)
+        out = H.dml_multiscale_head(z_list, (Hh, Ww), reciprocal_average=reciprocal_average, label_dtype=torch.uint8,
+                                    want_eds=True, eds_clamp=self.clamp, want_msp=self.want_msp, want_minmax=True,
+                                    gt=gt, confusion=confusion, confusion_shape=(self.K + 1, self.K), out=self._out)
+        self._out = out
+        conf = None
+        if self.store_conf:
+            if self._conf is None or self._conf.shape != out.eds.shape or self._conf.device != dev:
                 self._conf = torch.empty_like(out.eds)
             conf = self._conf
         res, stats = ood.eval_segments(out.eds, B, Hh * Ww, gt=gt, out_labels=self.out_labels, score_kind=0,

@@ -42,6 +42,18 @@ class PPMDeepsup_embedding(nn.Module):
         self.magnitude = magnitude
         self.centers = torch.eye(num_class) * magnitude   # plain attribute like the reference (:614)
 
+    def forward_lowres(self, conv_out):
+        """Stride-8 ``(logits, embedding)`` of :620-657, i.e. the eval branch WITHOUT the two full-resolution
+        ``F.interpolate`` calls of :659-669.  Feed the per-scale results to
+        ``dml_b200.anomaly.eval_ood.multiscale_scores`` / ``MultiScaleEvaluator``, which upsample, average
+        and score inside one kernel."""
+        conv5 = conv_out[-1]
+        size = conv5.shape[2:]
+        ppm_out = torch.cat([conv5] + [nn.functional.interpolate(p(conv5), size, mode='bilinear', align_corners=False)
+                                       for p in self.ppm], 1)
+        emb = self.conv_last(ppm_out)
+        return distance_logits(emb, magnitude=self.magnitude), emb
+
     def forward(self, conv_out, segSize=None, output_ft=True):
         conv5 = conv_out[-1]
         size = conv5.shape[2:]

@@ -139,7 +139,7 @@ int dml_head_forward(const dml_head_params* p, dml_stream_t stream_) {
   const long long hw = (long long)p->H * p->W;
   if (p->B == 0 || hw == 0) return DML_OK;
 
-  HeadArgs a;
+  HeadArgs a = {};
   a.x = p->x; a.mu = p->mu; a.diag_m = p->diag_m;
   a.msp_scale = 2.0f * p->diag_m * 1.4426950408889634f;
   a.first = p->score_first_class; a.clamp = p->eds_clamp;
@@ -170,6 +170,68 @@ int dml_head_forward(const dml_head_params* p, dml_stream_t stream_) {
   if (D <= 16) return head_dispatch_9_16(D, mode, vec, extra, a, stream);
   if (D <= 24) return head_dispatch_17_24(D, mode, vec, extra, a, stream);
   return head_dispatch_25_32(D, mode, vec, extra, a, stream);
+}
+
+int dml_multiscale_head_forward(const dml_multiscale_params* p, dml_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!p || p->struct_bytes != sizeof(dml_multiscale_params)) return DML_ERR_INVALID_ARG;
+  if (p->B < 0 || p->K < 1 || p->H < 0 || p->W < 0) return DML_ERR_INVALID_ARG;
+  if (p->n_scales < 1 || p->n_scales > HEAD_MAX_SCALES) return DML_ERR_INVALID_ARG;
+  if (p->K > DML_MAX_DIM) return DML_ERR_UNSUPPORTED_DIM;
+  if (p->score_first_class < 0 || p->score_first_class > 1 || p->score_first_class >= p->K) return DML_ERR_INVALID_ARG;
+  if ((p->want_eds_minmax || p->want_msp_minmax) && !p->minmax) return DML_ERR_INVALID_ARG;
+  if (p->confusion) {
+    if (!p->gt_u8 == !p->gt_i64) return DML_ERR_INVALID_ARG;
+    if (p->conf_rows < 1 || p->conf_cols < 1 || p->conf_rows * p->conf_cols > HEAD_MAX_CONF_BINS) return DML_ERR_INVALID_ARG;
+  }
+  if (p->B > 65535) return DML_ERR_INVALID_ARG;
+  if (p->B == 0 || p->H == 0 || p->W == 0) return DML_OK;
+  for (int s = 0; s < p->n_scales; ++s) {
+    if (!p->z[s] || p->h[s] < 1 || p->w[s] < 1) return DML_ERR_INVALID_ARG;
+    if ((long long)p->K * p->h[s] * p->w[s] > 0x7fffffffLL) return DML_ERR_INVALID_ARG;
+  }
+  const long long hw = (long long)p->H * p->W;
+
+  HeadArgs a = {};
+  a.first = p->score_first_class; a.clamp = p->eds_clamp;
+  a.logits = p->scores; a.label_u8 = p->label_u8; a.label_i64 = (long long*)p->label_i64;
+  a.maxlogit = p->maxlogit; a.eds = p->eds; a.msp = p->msp;
+  a.minmax = reinterpret_cast<int*>(p->minmax);
+  a.want_eds_mm = p->want_eds_minmax; a.want_msp_mm = p->want_msp_minmax;
+  a.gt_u8 = p->gt_u8; a.gt_i64 = (const long long*)p->gt_i64; a.conf = p->confusion;
+  a.crow = p->conf_rows; a.ccol = p->conf_cols;
+  a.B = p->B; a.K = p->K; a.HW = hw;
+  a.out_mask = (a.label_u8 ? OUT_LABEL_U8 : 0u) | (a.label_i64 ? OUT_LABEL_I64 : 0u) | (a.maxlogit ? OUT_MAXLOGIT : 0u) |
+               (a.eds ? OUT_EDS : 0u) | (a.msp ? OUT_MSP : 0u) |
+               ((a.minmax && (a.want_eds_mm || a.want_msp_mm)) ? OUT_MINMAX : 0u) | (a.conf ? OUT_CONF : 0u) |
+               (a.gt_u8 ? OUT_GT_U8 : 0u) | (a.logits ? OUT_LOGITS : 0u);
+  a.ms_n = p->n_scales; a.ms_W = p->W; a.ms_recip = p->reciprocal_average ? 1 : 0;
+  a.ms_div = (float)p->n_scales; a.ms_inv = 1.0f / (float)p->n_scales;
+  for (int s = 0; s < p->n_scales; ++s) {
+    a.ms_z[s] = p->z[s]; a.ms_h[s] = p->h[s]; a.ms_w[s] = p->w[s];
+    // torch area_pixel_compute_scale<float>(in, out, align_corners=false, nullopt) = float(in) / out
+    a.ms_rh[s] = (float)p->h[s] / (float)p->H;
+    a.ms_rw[s] = (float)p->w[s] / (float)p->W;
+  }
+  if (a.minmax && (a.want_eds_mm || a.want_msp_mm)) {
+    const int n4 = p->B * 4;
+    minmax_init_kernel<<<ceil_div_i(n4, 256), 256, 0, stream>>>(a.minmax, n4);
+    DML_LAUNCH_CHECK();
+  }
+  // VEC horizontally adjacent pixels per thread must stay inside one output row
+  auto al = [](const void* q, size_t n) { return q == nullptr || (reinterpret_cast<uintptr_t>(q) % n) == 0; };
+  int vec = 1;
+  if (p->W % 2 == 0 && al(p->scores, 8) && al(p->maxlogit, 8) && al(p->eds, 8) && al(p->msp, 8) && al(p->label_u8, 2) &&
+      al(p->label_i64, 16) && al(p->gt_u8, 2))
+    vec = 2;
+  if (const char* e = getenv("DML_MS_VEC")) {
+    if (atoi(e) == 1) vec = 1;
+  }
+  const int D = p->K;
+  if (D <= 8) return head_dispatch_1_8(D, HEAD_MS, vec, false, a, stream);
+  if (D <= 16) return head_dispatch_9_16(D, HEAD_MS, vec, false, a, stream);
+  if (D <= 24) return head_dispatch_17_24(D, HEAD_MS, vec, false, a, stream);
+  return head_dispatch_25_32(D, HEAD_MS, vec, false, a, stream);
 }
 
 int dml_scores_finalize(const float* eds, const float* msp, const float* minmax, int32_t B, int64_t hw, float lambda,

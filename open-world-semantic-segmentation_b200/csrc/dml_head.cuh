@@ -15,8 +15,11 @@ namespace dml {
 
 constexpr int HEAD_THREADS = 256;
 // prototype modes: dense [K,D] table; m*I fast path; input already holds the logits z (scores only)
-constexpr int HEAD_DENSE = 0, HEAD_IDENT = 1, HEAD_LOGITS = 2;
+// HEAD_MS: the logits are gathered on the fly from up to HEAD_MAX_SCALES low-resolution logit maps
+// (bilinear upsample, align_corners=False, averaged over the scales), then scored like HEAD_LOGITS
+constexpr int HEAD_DENSE = 0, HEAD_IDENT = 1, HEAD_LOGITS = 2, HEAD_MS = 3;
 constexpr int HEAD_MAX_NOVEL = 8;
+constexpr int HEAD_MAX_SCALES = DML_MAX_SCALES;
 constexpr int HEAD_MAX_CONF_BINS = 32 * 32;
 
 struct HeadArgs {
@@ -46,6 +49,13 @@ struct HeadArgs {
   int B, K;
   long long HW;
   unsigned out_mask;  // OUT_* bits: which outputs are wanted (hoists the pointer tests out of the kernel)
+  // HEAD_MS only: low-resolution maps [B,K,ms_h[s],ms_w[s]], fp32 source-index scales in/out
+  // (torch area_pixel_compute_scale), divisor = number of scales, output width
+  const float* ms_z[HEAD_MAX_SCALES];
+  int ms_h[HEAD_MAX_SCALES], ms_w[HEAD_MAX_SCALES];
+  float ms_rh[HEAD_MAX_SCALES], ms_rw[HEAD_MAX_SCALES];
+  int ms_n, ms_W, ms_recip;
+  float ms_div, ms_inv;
 };
 
 enum : unsigned { OUT_LABEL_U8 = 1u, OUT_LABEL_I64 = 2u, OUT_MAXLOGIT = 4u, OUT_EDS = 8u, OUT_MSP = 16u, OUT_MINMAX = 32u,
@@ -94,6 +104,65 @@ __device__ __forceinline__ double novel_neg_dist(const float (&x)[D][VEC], int v
   return -res;
 }
 
+// Multi-scale gather (anomaly/models/models.py:659-661 + anomaly/eval_ood_traditional.py:198-208):
+//   scores[k] = sum_s  bilinear_s(z_s[k]) / n_scales        (accumulated in scale order, fp32)
+// for VEC horizontally adjacent output pixels.  The arithmetic is torch's upsample_bilinear2d (source
+// index scale*(dst+0.5)-0.5 clamped at 0, lambda1 = src - floor, value = h0*(w0*v00 + w1*v01) +
+// h1*(w0*v10 + w1*v11)) with the FMA contraction pinned to the one the torch build evaluates --
+// src = fma(scale, dst+0.5, -0.5), t = fma(w0, v_0, w1*v_1), value = fma(h0, t0, h1*t1) -- which makes
+// the result bit-identical to torch's (checked against the CPU kernel in tests/).  The division by
+// the number of scales is correctly rounded (q = v*inv, one FMA residual correction: Markstein) like the
+// CPU `scores_tmp / 5`, or the plain multiplication by 1/n that torch's CUDA div-by-scalar kernel
+// performs (`ms_recip`).  The low-resolution maps are tiny (<= 0.5 MB per image and scale) and are
+// served by L1/L2; nothing of full resolution is read.
+template <int D, int VEC>
+__device__ __forceinline__ void ms_gather(const HeadArgs& a, int b, long long p0, float (&x)[D][VEC]) {
+  const int y = (int)(p0 / a.ms_W);
+  const int xo = (int)(p0 - (long long)y * a.ms_W);
+#pragma unroll
+  for (int d = 0; d < D; ++d)
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) x[d][v] = 0.f;
+#pragma unroll 1
+  for (int s = 0; s < a.ms_n; ++s) {
+    const int hs = a.ms_h[s], ws = a.ms_w[s];
+    float h1r = __fmaf_rn(a.ms_rh[s], y + 0.5f, -0.5f);
+    h1r = h1r < 0.f ? 0.f : h1r;
+    const int h1 = (int)h1r;
+    const int dy = (h1 < hs - 1) ? ws : 0;
+    const float h1l = h1r - h1, h0l = 1.0f - h1l;
+    int o00[VEC], dx[VEC];
+    float w1l[VEC], w0l[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      float w1r = __fmaf_rn(a.ms_rw[s], (xo + v) + 0.5f, -0.5f);
+      w1r = w1r < 0.f ? 0.f : w1r;
+      const int w1 = (int)w1r;
+      dx[v] = (w1 < ws - 1) ? 1 : 0;
+      w1l[v] = w1r - w1;
+      w0l[v] = 1.0f - w1l[v];
+      o00[v] = h1 * ws + w1;
+    }
+    const int plane = hs * ws;
+    const float* q = a.ms_z[s] + (long long)b * D * plane;
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) {
+        const float* r = q + o00[v];
+        const float v00 = __ldg(r), v01 = __ldg(r + dx[v]), v10 = __ldg(r + dy), v11 = __ldg(r + dy + dx[v]);
+        const float t0 = __fmaf_rn(w0l[v], v00, __fmul_rn(w1l[v], v01));
+        const float t1 = __fmaf_rn(w0l[v], v10, __fmul_rn(w1l[v], v11));
+        const float val = __fmaf_rn(h0l, t0, __fmul_rn(h1l, t1));
+        float t = __fmul_rn(val, a.ms_inv);
+        if (!a.ms_recip) t = __fmaf_rn(__fmaf_rn(-a.ms_div, t, val), a.ms_inv, t);
+        x[k][v] = __fadd_rn(x[k][v], t);
+      }
+      q += plane;
+    }
+  }
+}
+
 // Adds one observation to a block-shared histogram with a single shared-memory update per distinct
 // bin in the warp (segmentation labels are spatially coherent: usually 1-3 distinct bins per warp).
 __device__ __forceinline__ void warp_histogram_add(unsigned int* s_bins, int bin) {
@@ -116,7 +185,8 @@ __device__ __forceinline__ void warp_histogram_add(unsigned int* s_bins, int bin
 template <int D, int MODE, int VEC, bool EXTRA>
 __global__ void __launch_bounds__(HEAD_THREADS) head_kernel(const HeadArgs a) {
   constexpr bool IDENT = (MODE == HEAD_IDENT);
-  constexpr bool LOGITS = (MODE == HEAD_LOGITS);
+  constexpr bool MS = (MODE == HEAD_MS);
+  constexpr bool LOGITS = (MODE == HEAD_LOGITS) || MS;
   constexpr bool DENSE = (MODE == HEAD_DENSE);
   constexpr float LOG2E = 1.4426950408889634f;
   constexpr float PINF = __builtin_huge_valf();
@@ -148,7 +218,7 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_kernel(const HeadArgs a) {
   const bool skip0 = a.first != 0;
   const unsigned om = a.out_mask;
   const bool want_msp = (om & OUT_MSP) || a.want_msp_mm;
-  const float* x_img = a.x + ((long long)b * D) * a.HW;
+  const float* x_img = MS ? nullptr : a.x + ((long long)b * D) * a.HW;
   // running per-thread min / max of the score maps (int order == float order for values >= 0)
   int emin = 0x7fffffff, emax = (int)0x80000000, mmin = 0x7fffffff, mmax = (int)0x80000000;
 
@@ -158,7 +228,27 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_kernel(const HeadArgs a) {
   const bool active = p0 < a.HW;
 
   float x[D][VEC];
-  {
+  if constexpr (MS) {
+    if (active) {
+      ms_gather<D, VEC>(a, b, p0, x);
+    } else {
+#pragma unroll
+      for (int d = 0; d < D; ++d)
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) x[d][v] = 0.f;
+    }
+    // optional store of the averaged full-resolution maps (the reference's `scores` / `ft1`)
+    if ((om & OUT_LOGITS) && active) {
+      float* lgm = a.logits + ((long long)b * D) * a.HW + p0;
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        FVec<VEC> t;
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) t.v[v] = x[d][v];
+        st_stream<VEC>(lgm + (long long)d * a.HW, t);
+      }
+    }
+  } else {
     const float* q = x_img + p0;
 #pragma unroll
     for (int d = 0; d < D; ++d) {
@@ -492,6 +582,8 @@ int launch_head(const HeadArgs& a, cudaStream_t stream) {
 #define DML_HEAD_CASE(Dv)                                                                      \
   case Dv:                                                                                     \
     if (mode == HEAD_IDENT) { DML_HEAD_CASE_I(Dv, HEAD_IDENT) }                                \
+    if (mode == HEAD_MS)                                                                       \
+      return vec >= 2 ? launch_head<Dv, HEAD_MS, 2, false>(a, s) : launch_head<Dv, HEAD_MS, 1, false>(a, s); \
     if (mode == HEAD_LOGITS)                                                                   \
       return vec == 4 ? launch_head<Dv, HEAD_LOGITS, 4, false>(a, s) : vec == 2 ? launch_head<Dv, HEAD_LOGITS, 2, false>(a, s) : launch_head<Dv, HEAD_LOGITS, 1, false>(a, s); \
     DML_HEAD_CASE_I(Dv, HEAD_DENSE)

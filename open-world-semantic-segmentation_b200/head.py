@@ -15,7 +15,7 @@ from typing import Optional
 import torch
 
 from . import _lib
-from ._lib import HeadParams, check, lib, ptr, require_cuda, stream_ptr
+from ._lib import HeadParams, MultiscaleParams, check, lib, ptr, require_cuda, stream_ptr
 
 DEFAULT_MAGNITUDE = 3.0          # anomaly/models/models.py:615, network/utils.py:104
 CLAMP_ANOMALY = 400.0            # anomaly/eval_ood_traditional.py:304
@@ -163,6 +163,113 @@ def dml_head(x: torch.Tensor, centers: Optional[torch.Tensor] = None, magnitude:
     with torch.cuda.device(dev):
         check(lib().dml_head_forward(C.byref(p), stream_ptr(dev)), "dml_head_forward")
     return o
+
+
+def dml_multiscale_head(z_list, size, *, reciprocal_average: bool = False, want_scores: bool = False,
+                        label_dtype: Optional[torch.dtype] = torch.uint8, want_maxlogit: bool = False,
+                        want_eds: bool = False, eds_clamp: float = 0.0, want_msp: bool = False,
+                        want_minmax: bool = False, exclude_back: bool = False, gt: Optional[torch.Tensor] = None,
+                        confusion: Optional[torch.Tensor] = None, confusion_shape: Optional[tuple] = None,
+                        out: Optional[HeadOutput] = None) -> HeadOutput:
+    """Fused multi-scale upsample + average + score head (``dml_multiscale_head_forward``).
+
+    ``z_list``: per scale the stride-8 logits [B,K,h_s,w_s] (fp32, CUDA); ``size`` = (H, W) = ``segSize``.
+    Equivalent to the reference loop ``scores += F.interpolate(z_s, segSize, 'bilinear',
+    align_corners=False) / len(z_list)`` (anomaly/models/models.py:659-661,
+    anomaly/eval_ood_traditional.py:192-208) followed by the score lines (:212-218,276-305,434), but no
+    full-resolution [B,K,H,W] tensor is read or -- unless ``want_scores`` -- written.
+    ``reciprocal_average``: multiply by fl(1/S) like torch's CUDA division-by-scalar kernel instead of
+    the correctly rounded division torch performs on the CPU.
+    ``out.logits`` holds the averaged ``scores`` when ``want_scores``."""
+    if not 1 <= len(z_list) <= _lib.MAX_SCALES:
+        raise ValueError(f"between 1 and {_lib.MAX_SCALES} scales are supported")
+    zs = []
+    for z in z_list:
+        require_cuda(z, "z")
+        if z.dtype != torch.float32 or z.dim() != 4:
+            raise ValueError("every scale must be a float32 [B,K,h,w] tensor")
+        zs.append(z.contiguous())
+    B, K = zs[0].shape[:2]
+    dev = zs[0].device
+    for z in zs:
+        if z.shape[0] != B or z.shape[1] != K or z.device != dev:
+            raise ValueError("scales differ in batch size, class count or device")
+    H, W = int(size[0]), int(size[1])
+    o = out or HeadOutput()
+
+    def buf(cur, shape, dtype):
+        if cur is not None:
+            if tuple(cur.shape) != tuple(shape) or cur.dtype != dtype or cur.device != dev:
+                raise ValueError("preallocated output has the wrong shape/dtype/device")
+            return cur
+        return torch.empty(shape, dtype=dtype, device=dev)
+
+    p = MultiscaleParams()
+    p.struct_bytes = C.sizeof(MultiscaleParams)
+    p.B, p.K, p.H, p.W = B, K, H, W
+    p.n_scales = len(zs)
+    for s, z in enumerate(zs):
+        p.z[s] = z.data_ptr()
+        p.h[s], p.w[s] = z.shape[2], z.shape[3]
+    p.reciprocal_average = 1 if reciprocal_average else 0
+    p.score_first_class = 1 if exclude_back else 0
+    p.eds_clamp = eds_clamp
+    if want_scores:
+        o.logits = buf(o.logits, (B, K, H, W), torch.float32)
+        p.scores = o.logits.data_ptr()
+    if label_dtype is not None:
+        if label_dtype not in (torch.uint8, torch.int64):
+            raise ValueError("label_dtype must be torch.uint8, torch.int64 or None")
+        o.label = buf(o.label, (B, H, W), label_dtype)
+        if label_dtype == torch.uint8:
+            p.label_u8 = o.label.data_ptr()
+        else:
+            p.label_i64 = o.label.data_ptr()
+    if want_maxlogit:
+        o.maxlogit = buf(o.maxlogit, (B, H, W), torch.float32)
+        p.maxlogit = o.maxlogit.data_ptr()
+    if want_eds:
+        o.eds = buf(o.eds, (B, H, W), torch.float32)
+        p.eds = o.eds.data_ptr()
+    if want_msp:
+        o.msp = buf(o.msp, (B, H, W), torch.float32)
+        p.msp = o.msp.data_ptr()
+    if want_minmax:
+        o.minmax = buf(o.minmax, (B, 4), torch.float32)
+        p.minmax = o.minmax.data_ptr()
+        p.want_eds_minmax = 1 if want_eds else 0
+        p.want_msp_minmax = 1 if want_msp else 0
+    if gt is not None:
+        require_cuda(gt, "gt")
+        gt = gt.contiguous()
+        if tuple(gt.shape) != (B, H, W) or gt.dtype not in (torch.uint8, torch.int64):
+            raise ValueError("gt must be a [B,H,W] uint8 or int64 tensor")
+        if confusion is None:
+            if o.confusion is not None:
+                confusion = o.confusion
+            else:
+                rows, cols = confusion_shape or (K + 1, K)
+                confusion = torch.zeros(rows, cols, dtype=torch.int64, device=dev)
+        if confusion.dtype != torch.int64 or confusion.dim() != 2 or not confusion.is_contiguous():
+            raise ValueError("confusion must be a contiguous int64 [rows, cols] tensor")
+        o.confusion = confusion
+        p.confusion = confusion.data_ptr()
+        p.conf_rows, p.conf_cols = confusion.shape
+        if gt.dtype == torch.uint8:
+            p.gt_u8 = gt.data_ptr()
+        else:
+            p.gt_i64 = gt.data_ptr()
+    with torch.cuda.device(dev):
+        check(lib().dml_multiscale_head_forward(C.byref(p), stream_ptr(dev)), "dml_multiscale_head_forward")
+    return o
+
+
+def multiscale_average(x_list, size, *, reciprocal_average: bool = False, out: Optional[torch.Tensor] = None):
+    """``sum_s F.interpolate(x_s, size, 'bilinear', align_corners=False) / S`` in the reference's order
+    (the ``ft1`` accumulator of anomaly/eval_ood_traditional.py:194-196,209-210): [B,C,H,W]."""
+    o = HeadOutput(logits=out)
+    return dml_multiscale_head(x_list, size, reciprocal_average=reciprocal_average, want_scores=True,
+                               label_dtype=None, out=o).logits
 
 
 def finalize_scores(eds: Optional[torch.Tensor], msp: Optional[torch.Tensor], minmax: torch.Tensor, *,

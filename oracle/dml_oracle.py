@@ -91,8 +91,9 @@ def multiscale_scores(x_lows, centers: torch.Tensor, seg_size):
     (anomaly/eval_ood_traditional.py:192-210)."""
     n = len(x_lows)
     k = centers.shape[0]
-    scores = torch.zeros(1, k, seg_size[0], seg_size[1])
-    ft = torch.zeros(1, x_lows[0].shape[1], seg_size[0], seg_size[1])
+    b = x_lows[0].shape[0]
+    scores = torch.zeros(b, k, seg_size[0], seg_size[1])
+    ft = torch.zeros(b, x_lows[0].shape[1], seg_size[0], seg_size[1])
     for x_low in x_lows:
         z_up, f_up = ppm_head_eval(x_low, centers, seg_size)
         scores = scores + z_up / n

@@ -54,10 +54,32 @@ def test_struct_layouts_match_the_header():
     assert ctypes.sizeof(_lib.OodResult) == 56
 
 
+def test_multiscale_struct_layout_matches_the_header():
+    from dml_b200 import _lib
+    text = open(os.path.join(ROOT, "include", "dml_b200.h")).read()
+    start = text.index("typedef struct dml_multiscale_params {") + len("typedef struct dml_multiscale_params {")
+    body = re.sub(r"/\*.*?\*/", "", text[start:text.index("} dml_multiscale_params;")], flags=re.S)
+    fields = []
+    for decl in body.split(";"):
+        decl = decl.strip()
+        if not decl:
+            continue
+        names = decl.split(",")
+        fields.append(names[0].split()[-1].lstrip("*"))
+        fields.extend(n.strip().lstrip("*") for n in names[1:])
+    fields = [re.sub(r"\[.*\]", "", f) for f in fields]
+    assert [f[0] for f in _lib.MultiscaleParams._fields_] == fields
+    assert _lib.MAX_SCALES == int(re.search(r"#define DML_MAX_SCALES (\d+)", text).group(1))
+    # 5 x i32 + pad, 8 pointers, 16 x i32, 3 x 4-byte scalars + pad, 7 pointers, 2 x i32, 3 pointers, 2 x i32
+    assert ctypes.sizeof(_lib.MultiscaleParams) == 24 + 64 + 64 + 16 + 56 + 8 + 24 + 8
+
+
 def test_no_cpu_fallback():
     import dml_b200
     with pytest.raises(dml_b200.DmlError):
         dml_b200.dml_head(torch.zeros(1, 13, 4, 4))
+    with pytest.raises(dml_b200.DmlError):
+        dml_b200.dml_multiscale_head([torch.zeros(1, 13, 4, 4)], (8, 8))
     from dml_b200 import ood
     with pytest.raises(dml_b200.DmlError):
         ood.eval_segments(torch.zeros(8), 1, 8, gt=torch.zeros(8, dtype=torch.uint8))
