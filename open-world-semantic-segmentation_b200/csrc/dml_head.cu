@@ -1,5 +1,6 @@
 // C-ABI entry points of the head path: dml_head_forward, dml_scores_finalize, dml_confusion,
 // dml_plm_merge, plus library-level helpers.  Kernel body lives in dml_head.cuh.
+#include <cmath>
 #include <cstdlib>
 #include "dml_head.cuh"
 
@@ -228,10 +229,31 @@ int dml_multiscale_head_forward(const dml_multiscale_params* p, dml_stream_t str
     if (atoi(e) == 1) vec = 1;
   }
   const int D = p->K;
-  if (D <= 8) return head_dispatch_1_8(D, HEAD_MS, vec, false, a, stream);
-  if (D <= 16) return head_dispatch_9_16(D, HEAD_MS, vec, false, a, stream);
-  if (D <= 24) return head_dispatch_17_24(D, HEAD_MS, vec, false, a, stream);
-  return head_dispatch_25_32(D, HEAD_MS, vec, false, a, stream);
+  // staged variant: the low-resolution footprint of a 16 x (64*vec) output tile, all scales, must fit in the
+  // default 48 KB of dynamic shared memory (always true for up-sampling by >= ~3x); otherwise gather from L1/L2
+  int mode = HEAD_MSS;
+  {
+    const int tile_w = MS_TILE_THREADS_X * vec;
+    long long floats = 0;
+    for (int s = 0; s < p->n_scales; ++s) {
+      // rows spanned by the taps of MS_TILE_ROWS consecutive outputs: ceil(scale*(rows-1)) + 2, +1 for fp32 rounding
+      const int fh = (int)fmin((double)p->h[s], ceil((double)a.ms_rh[s] * (MS_TILE_ROWS - 1)) + 3.0);
+      const int fw = (int)fmin((double)p->w[s], ceil((double)a.ms_rw[s] * (tile_w - 1)) + 3.0);
+      a.ms_fh[s] = fh; a.ms_fw[s] = fw; a.ms_soff[s] = (int)floats;
+      floats += (long long)fh * fw * ms_stride(D);
+    }
+    const size_t conf_bytes = p->confusion ? (((size_t)p->conf_rows * p->conf_cols * sizeof(unsigned) + 15) & ~(size_t)15) : 0;
+    if (floats * 4 + (long long)conf_bytes > 48 * 1024 - 64) mode = HEAD_MS;
+    a.ms_smem_floats = (int)floats;
+    a.ms_H = p->H;
+    if (const char* e = getenv("DML_MS_DIRECT")) {
+      if (atoi(e) == 1) mode = HEAD_MS;
+    }
+  }
+  if (D <= 8) return head_dispatch_1_8(D, mode, vec, false, a, stream);
+  if (D <= 16) return head_dispatch_9_16(D, mode, vec, false, a, stream);
+  if (D <= 24) return head_dispatch_17_24(D, mode, vec, false, a, stream);
+  return head_dispatch_25_32(D, mode, vec, false, a, stream);
 }
 
 int dml_scores_finalize(const float* eds, const float* msp, const float* minmax, int32_t B, int64_t hw, float lambda,

@@ -17,7 +17,14 @@ constexpr int HEAD_THREADS = 256;
 // prototype modes: dense [K,D] table; m*I fast path; input already holds the logits z (scores only)
 // HEAD_MS: the logits are gathered on the fly from up to HEAD_MAX_SCALES low-resolution logit maps
 // (bilinear upsample, align_corners=False, averaged over the scales), then scored like HEAD_LOGITS
-constexpr int HEAD_DENSE = 0, HEAD_IDENT = 1, HEAD_LOGITS = 2, HEAD_MS = 3;
+// HEAD_MSS: same, but every CTA owns a 2-D output tile and first stages the low-resolution footprint of
+// all scales in shared memory (class-innermost, 16-byte vector reads, immediate class offsets)
+constexpr int HEAD_DENSE = 0, HEAD_IDENT = 1, HEAD_LOGITS = 2, HEAD_MS = 3, HEAD_MSS = 4;
+constexpr int MS_TILE_THREADS_X = 64;                      // threads per output row of a CTA tile
+constexpr int MS_TILE_ROWS = 16;                           // output rows per CTA tile (4 per tile-loop iteration)
+// shared-memory stride (floats) of one staged low-resolution pixel: classes padded to a multiple of 4 and the
+// stride kept == 4 (mod 8) so that 8 neighbouring pixels fall into 8 disjoint 4-bank groups (conflict-free LDS.128)
+__host__ __device__ constexpr int ms_stride(int D) { return (((D + 3) / 4) & 1) ? ((D + 3) & ~3) : ((D + 3) & ~3) + 4; }
 constexpr int HEAD_MAX_NOVEL = 8;
 constexpr int HEAD_MAX_SCALES = DML_MAX_SCALES;
 constexpr int HEAD_MAX_CONF_BINS = 32 * 32;
@@ -56,6 +63,9 @@ struct HeadArgs {
   float ms_rh[HEAD_MAX_SCALES], ms_rw[HEAD_MAX_SCALES];
   int ms_n, ms_W, ms_recip;
   float ms_div, ms_inv;
+  // HEAD_MSS only: output height, per-scale staged footprint (rows, cols, float offset in shared memory)
+  int ms_H, ms_smem_floats;
+  int ms_fh[HEAD_MAX_SCALES], ms_fw[HEAD_MAX_SCALES], ms_soff[HEAD_MAX_SCALES];
 };
 
 enum : unsigned { OUT_LABEL_U8 = 1u, OUT_LABEL_I64 = 2u, OUT_MAXLOGIT = 4u, OUT_EDS = 8u, OUT_MSP = 16u, OUT_MINMAX = 32u,
@@ -163,6 +173,107 @@ __device__ __forceinline__ void ms_gather(const HeadArgs& a, int b, long long p0
   }
 }
 
+// floor of torch's bilinear source index for output coordinate `dst` (same fp32 arithmetic as the taps)
+__device__ __forceinline__ int ms_src_floor(float scale, int dst) {
+  float r = __fmaf_rn(scale, dst + 0.5f, -0.5f);
+  r = r < 0.f ? 0.f : r;
+  return (int)r;
+}
+
+// HEAD_MSS stage 1: copy the low-resolution footprint of the CTA's output tile (origin ty0, tx0) into shared
+// memory for every scale, laid out [row][col][ms_stride(D)] (class innermost).  Rows / columns past the map
+// edge are clamped duplicates that no tap addresses.
+template <int D>
+__device__ __forceinline__ void ms_stage(const HeadArgs& a, int b, int ty0, int tx0, float* s_ms) {
+  constexpr int ST = ms_stride(D);
+  for (int s = 0; s < a.ms_n; ++s) {
+    const int hs = a.ms_h[s], ws = a.ms_w[s], fh = a.ms_fh[s], fw = a.ms_fw[s];
+    const int r0 = ms_src_floor(a.ms_rh[s], ty0), c0 = ms_src_floor(a.ms_rw[s], tx0);
+    const float* zb = a.ms_z[s] + (long long)b * D * hs * ws;
+    float* S = s_ms + a.ms_soff[s];
+    const int n = fh * fw;
+    // one staged pixel per thread and step (a single integer division), its D classes in the inner loop:
+    // consecutive threads read consecutive columns of one class plane
+    for (int rc = threadIdx.x; rc < n; rc += HEAD_THREADS) {
+      const int r = rc / fw, c = rc - r * fw;
+      const float* src = zb + min(r0 + r, hs - 1) * ws + min(c0 + c, ws - 1);
+      float* dst = S + rc * ST;
+#pragma unroll
+      for (int k = 0; k < D; ++k) dst[k] = __ldg(src + k * hs * ws);
+    }
+  }
+}
+
+// HEAD_MSS stage 2: the arithmetic of ms_gather with the four taps read from the staged footprint
+// (ceil(D/4) 16-byte shared-memory loads per tap, class offsets are immediates).  Classes are processed
+// two at a time with sm_100's packed fp32 instructions (FMUL2 / FFMA2 / FADD2: the same IEEE round-to-nearest
+// result per lane, half the issue slots); the odd lane of the last pair is padding and is dropped.
+template <int D, int VEC>
+__device__ __forceinline__ void ms_gather_staged(const HeadArgs& a, const float* s_ms, int ty0, int tx0, int y, int xo,
+                                                 float (&x)[D][VEC]) {
+  constexpr int ST = ms_stride(D);
+  constexpr int NQ = (D + 3) / 4;
+  constexpr int NP = (D + 1) / 2;
+  f32x2 acc[NP][VEC];
+#pragma unroll
+  for (int p = 0; p < NP; ++p)
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) acc[p][v] = 0ull;
+  const f32x2 inv2 = pack2(a.ms_inv, a.ms_inv), ndiv2 = pack2(-a.ms_div, -a.ms_div);
+  const bool recip = a.ms_recip != 0;
+#pragma unroll 1
+  for (int s = 0; s < a.ms_n; ++s) {
+    const int hs = a.ms_h[s], ws = a.ms_w[s], fw = a.ms_fw[s];
+    const int r0 = ms_src_floor(a.ms_rh[s], ty0), c0 = ms_src_floor(a.ms_rw[s], tx0);
+    float h1r = __fmaf_rn(a.ms_rh[s], y + 0.5f, -0.5f);
+    h1r = h1r < 0.f ? 0.f : h1r;
+    const int h1 = (int)h1r;
+    const int dy = (h1 < hs - 1) ? fw * ST : 0;
+    const float h1l = h1r - h1, h0l = 1.0f - h1l;
+    const f32x2 h0 = pack2(h0l, h0l), h1p = pack2(h1l, h1l);
+    const float* S = s_ms + a.ms_soff[s] + (h1 - r0) * fw * ST;
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      float w1r = __fmaf_rn(a.ms_rw[s], (xo + v) + 0.5f, -0.5f);
+      w1r = w1r < 0.f ? 0.f : w1r;
+      const int w1 = (int)w1r;
+      const int dx = (w1 < ws - 1) ? ST : 0;
+      const float w1l = w1r - w1, w0l = 1.0f - w1l;
+      const f32x2 w0 = pack2(w0l, w0l), w1p = pack2(w1l, w1l);
+      const ulonglong2* p00 = reinterpret_cast<const ulonglong2*>(S + (w1 - c0) * ST);
+      const ulonglong2* p01 = reinterpret_cast<const ulonglong2*>(S + (w1 - c0) * ST + dx);
+      const ulonglong2* p10 = reinterpret_cast<const ulonglong2*>(S + (w1 - c0) * ST + dy);
+      const ulonglong2* p11 = reinterpret_cast<const ulonglong2*>(S + (w1 - c0) * ST + dy + dx);
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) {
+        const ulonglong2 a00 = p00[q], a01 = p01[q], a10 = p10[q], a11 = p11[q];
+        const f32x2 v00[2] = {a00.x, a00.y}, v01[2] = {a01.x, a01.y}, v10[2] = {a10.x, a10.y}, v11[2] = {a11.x, a11.y};
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int p = 2 * q + j;
+          if (p < NP) {
+            const f32x2 t0 = fma2_rn(w0, v00[j], mul2_rn(w1p, v01[j]));
+            const f32x2 t1 = fma2_rn(w0, v10[j], mul2_rn(w1p, v11[j]));
+            const f32x2 val = fma2_rn(h0, t0, mul2_rn(h1p, t1));
+            f32x2 t = mul2_rn(val, inv2);
+            if (!recip) t = fma2_rn(fma2_rn(ndiv2, t, val), inv2, t);
+            acc[p][v] = add2_rn(acc[p][v], t);
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int p = 0; p < NP; ++p)
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      float lo, hi;
+      unpack2(acc[p][v], lo, hi);
+      x[2 * p][v] = lo;
+      if (2 * p + 1 < D) x[2 * p + 1][v] = hi;
+    }
+}
+
 // Adds one observation to a block-shared histogram with a single shared-memory update per distinct
 // bin in the warp (segmentation labels are spatially coherent: usually 1-3 distinct bins per warp).
 __device__ __forceinline__ void warp_histogram_add(unsigned int* s_bins, int bin) {
@@ -185,7 +296,8 @@ __device__ __forceinline__ void warp_histogram_add(unsigned int* s_bins, int bin
 template <int D, int MODE, int VEC, bool EXTRA>
 __global__ void __launch_bounds__(HEAD_THREADS) head_kernel(const HeadArgs a) {
   constexpr bool IDENT = (MODE == HEAD_IDENT);
-  constexpr bool MS = (MODE == HEAD_MS);
+  constexpr bool MSS = (MODE == HEAD_MSS);
+  constexpr bool MS = (MODE == HEAD_MS) || MSS;
   constexpr bool LOGITS = (MODE == HEAD_LOGITS) || MS;
   constexpr bool DENSE = (MODE == HEAD_DENSE);
   constexpr float LOG2E = 1.4426950408889634f;
@@ -211,9 +323,20 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_kernel(const HeadArgs a) {
     }
   }
   for (int i = threadIdx.x; i < nbins; i += HEAD_THREADS) s_conf[i] = 0u;
-  if ((EXTRA && n_novel > 0) || DENSE || nbins > 0) __syncthreads();
-
   const int b = blockIdx.y;
+  // HEAD_MSS: 2-D output tile of MS_TILE_ROWS x (MS_TILE_THREADS_X * VEC) pixels per CTA
+  int ms_ty0 = 0, ms_tx0 = 0;
+  float* s_ms = nullptr;
+  if constexpr (MSS) {
+    const int tiles_x = (a.ms_W + MS_TILE_THREADS_X * VEC - 1) / (MS_TILE_THREADS_X * VEC);
+    const int tile_y = blockIdx.x / tiles_x;
+    ms_ty0 = tile_y * MS_TILE_ROWS;
+    ms_tx0 = (blockIdx.x - tile_y * tiles_x) * (MS_TILE_THREADS_X * VEC);
+    s_ms = reinterpret_cast<float*>(smem_dyn + (((size_t)nbins * sizeof(unsigned) + 15) & ~(size_t)15));
+    ms_stage<D>(a, b, ms_ty0, ms_tx0, s_ms);
+  }
+  if ((EXTRA && n_novel > 0) || DENSE || nbins > 0 || MSS) __syncthreads();
+
   const uint64_t pol = policy_evict_first();
   const bool skip0 = a.first != 0;
   const unsigned om = a.out_mask;
@@ -224,13 +347,25 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_kernel(const HeadArgs a) {
 
 #pragma unroll 1
   for (int it = 0; it < HEAD_TILES_PER_BLOCK; ++it) {
-  const long long p0 = (((long long)blockIdx.x * HEAD_TILES_PER_BLOCK + it) * HEAD_THREADS + threadIdx.x) * VEC;
-  const bool active = p0 < a.HW;
+  long long p0;
+  bool active;
+  int ms_y = 0, ms_x = 0;
+  if constexpr (MSS) {
+    static_assert(HEAD_THREADS / MS_TILE_THREADS_X * HEAD_TILES_PER_BLOCK == MS_TILE_ROWS, "tile shape");
+    ms_y = ms_ty0 + it * (HEAD_THREADS / MS_TILE_THREADS_X) + (threadIdx.x / MS_TILE_THREADS_X);
+    ms_x = ms_tx0 + (threadIdx.x % MS_TILE_THREADS_X) * VEC;
+    active = ms_y < a.ms_H && ms_x < a.ms_W;
+    p0 = (long long)ms_y * a.ms_W + ms_x;
+  } else {
+    p0 = (((long long)blockIdx.x * HEAD_TILES_PER_BLOCK + it) * HEAD_THREADS + threadIdx.x) * VEC;
+    active = p0 < a.HW;
+  }
 
   float x[D][VEC];
   if constexpr (MS) {
     if (active) {
-      ms_gather<D, VEC>(a, b, p0, x);
+      if constexpr (MSS) ms_gather_staged<D, VEC>(a, s_ms, ms_ty0, ms_tx0, ms_y, ms_x, x);
+      else ms_gather<D, VEC>(a, b, p0, x);
     } else {
 #pragma unroll
       for (int d = 0; d < D; ++d)
@@ -570,6 +705,12 @@ int launch_head(const HeadArgs& a, cudaStream_t stream) {
   dim3 grid((unsigned)((a.HW + per_block - 1) / per_block), (unsigned)a.B);
   size_t smem = (EXTRA ? (size_t)a.n_novel * D * sizeof(double) : 0) + (MODE == HEAD_DENSE ? (size_t)a.K * DP * sizeof(float) : 0) +
                 (a.conf ? (size_t)a.crow * a.ccol * sizeof(unsigned) : 0);
+  if constexpr (MODE == HEAD_MSS) {
+    const int tiles_x = (a.ms_W + MS_TILE_THREADS_X * VEC - 1) / (MS_TILE_THREADS_X * VEC);
+    const int tiles_y = (a.ms_H + MS_TILE_ROWS - 1) / MS_TILE_ROWS;
+    grid.x = (unsigned)(tiles_x * tiles_y);
+    smem = ((smem + 15) & ~(size_t)15) + (size_t)a.ms_smem_floats * sizeof(float);
+  }
   head_kernel<D, MODE, VEC, EXTRA><<<grid, HEAD_THREADS, smem, stream>>>(a);
   DML_LAUNCH_CHECK();
   return DML_OK;
@@ -584,6 +725,8 @@ int launch_head(const HeadArgs& a, cudaStream_t stream) {
     if (mode == HEAD_IDENT) { DML_HEAD_CASE_I(Dv, HEAD_IDENT) }                                \
     if (mode == HEAD_MS)                                                                       \
       return vec >= 2 ? launch_head<Dv, HEAD_MS, 2, false>(a, s) : launch_head<Dv, HEAD_MS, 1, false>(a, s); \
+    if (mode == HEAD_MSS)                                                                      \
+      return vec >= 2 ? launch_head<Dv, HEAD_MSS, 2, false>(a, s) : launch_head<Dv, HEAD_MSS, 1, false>(a, s); \
     if (mode == HEAD_LOGITS)                                                                   \
       return vec == 4 ? launch_head<Dv, HEAD_LOGITS, 4, false>(a, s) : vec == 2 ? launch_head<Dv, HEAD_LOGITS, 2, false>(a, s) : launch_head<Dv, HEAD_LOGITS, 1, false>(a, s); \
     DML_HEAD_CASE_I(Dv, HEAD_DENSE)

@@ -31,7 +31,9 @@ def main():
     torch.cuda.set_device(dev)
     g = torch.Generator(device=dev).manual_seed(0)
     embs = [torch.randn(B, K, h, w, generator=g, device=dev) * 0.7 + 1.0 for (h, w) in SH_SCALES]
-    gt = torch.randint(0, K + 1, (B, *size), generator=g, device=dev).to(torch.uint8)
+    # spatially coherent ground truth (64x64 blocks), like real label maps and like bench.py's synthetic data
+    gt = torch.randint(0, K + 1, (B, (size[0] + 63) // 64, (size[1] + 63) // 64), generator=g, device=dev)
+    gt = gt.repeat_interleave(64, 1).repeat_interleave(64, 2)[:, :size[0], :size[1]].contiguous().to(torch.uint8)
     out = H.HeadOutput()
     lows = [H.HeadOutput() for _ in embs]
     conf = torch.zeros(K + 1, K, dtype=torch.int64, device=dev)
