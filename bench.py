@@ -331,6 +331,9 @@ def run_ours(args):
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
     if world > 1:
+        # keep stdout to the ONE JSON line: NCCL prints its version banner to stdout at NCCL_DEBUG=VERSION
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=device)
     lib = dml_b200.load_library()
     k, h, w, n = args.classes, args.height, args.width, args.images

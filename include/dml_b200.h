@@ -286,6 +286,16 @@ DML_API int dml_ood_scan_range(const uint32_t* sorted_keys, int64_t n, const lon
                        double recall_level, void* workspace, size_t workspace_bytes, void* partial_out,
                        dml_stream_t stream);
 
+/* "partition" exchange mode of the multi-GPU pooled metric: scatter UNSORTED packed keys into n_buckets
+ * contiguous key ranges (one per rank), ship range r to rank r, sort only what is received -- one partition
+ * pass instead of one full local sort.  bucket(key) = #{ j : key >= bounds[j] } with `bounds` a DEVICE
+ * array of n_buckets-1 ascending keys; out = [bucket 0 | bucket 1 | ...] (order inside a bucket
+ * unspecified), counts (device, [n_buckets] int64) = exact bucket sizes.  1 <= n_buckets <= DML_MAX_PARTITIONS. */
+#define DML_MAX_PARTITIONS 16
+DML_API size_t dml_ood_partition_workspace_bytes(int32_t n_buckets);
+DML_API int dml_ood_partition(const uint32_t* keys, int64_t n, const uint32_t* bounds, int32_t n_buckets, uint32_t* out,
+                      long long* counts, void* workspace, size_t workspace_bytes, dml_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

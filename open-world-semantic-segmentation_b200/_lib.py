@@ -99,6 +99,9 @@ SIGNATURES = {
                                         C.c_size_t, C.c_void_p, C.c_void_p]),
     "dml_ood_sort": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_size_t,
                                C.POINTER(C.c_void_p), C.c_void_p]),
+    "dml_ood_partition_workspace_bytes": (C.c_size_t, [C.c_int32]),
+    "dml_ood_partition": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_size_t, C.c_void_p]),
     "dml_ood_lower_bound": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "dml_ood_count_positive": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "dml_ood_scan_range": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_double, C.c_void_p, C.c_size_t,

@@ -7,11 +7,14 @@ data-path collective; only the pooled ranking needs an exchange:
   2. G-1 splitters are chosen from an all-gathered regular sample of the sorted shards
      (splitters have the positive bit cleared, so one score value never straddles two ranges);
   3. exchange of the locally SORTED shards:
-       * ``mode="alltoall"`` (default): rank r receives only key range r from every peer
+       * ``mode="alltoall"``: rank r receives only key range r from every peer
          (NCCL all_to_all_single with uneven splits; each rank moves ~n/G keys);
        * ``mode="allgather"``: every rank receives every sorted shard (the contract form of the
          north star: "locally sorted shards merged through an NCCL allgather") and cuts its own
          key range out of each;
+     or, ``mode="partition"`` (default, fastest): steps 1-3 without the local sort -- splitters come from
+     a strided sample of the UNSORTED keys, ``dml_ood_partition`` scatters the keys into the G ranges
+     (one 12 B/key pass instead of a 36 B/key sort) and range r travels to rank r by all-to-all;
   4. the G sorted runs of a range are merged by one more local radix sort, the positives /
      elements that precede the range are all-gathered (2 integers per rank) and the range is scanned
      with those carried counts (``dml_ood_scan_range``);
@@ -33,6 +36,7 @@ import torch.distributed as dist
 from . import ood
 
 SAMPLES_PER_RANK = 4096
+PARTITION_SAMPLES_PER_RANK = 16384   # unsorted shards: a larger sample keeps the ranges balanced to ~1 %
 
 
 class CudaOps:
@@ -111,6 +115,30 @@ class CudaOps:
     def empty_keys(self, n, tag):
         return self.ws.get("d_recv_" + tag, 4 * max(n, 1)).view(torch.int32)[:n]
 
+    def sample_unsorted(self, keys, n_samples):
+        """strided sample of unsorted keys (int32 bit patterns; -1 marks an empty shard)"""
+        n = keys.numel()
+        if n == 0:
+            return torch.full((n_samples,), -1, dtype=torch.int32, device=self.device)
+        idx = (torch.arange(n_samples, device=self.device, dtype=torch.float64) + 0.5) * (n / n_samples)
+        return keys[idx.long().clamp_(max=n - 1)]
+
+    def partition(self, keys, inner_bounds):
+        """keys (unsorted) -> (keys grouped by range, int64 counts [G]); inner_bounds: int32 bit patterns of the
+        G-1 ascending range starts b_1..b_{G-1}"""
+        from ._lib import check, lib, ptr, stream_ptr
+        n = keys.numel()
+        G = inner_bounds.numel() + 1
+        out = self.ws.get("d_part", 4 * max(n, 1)).view(torch.int32)[:n]
+        counts = torch.empty(G, dtype=torch.int64, device=self.device)
+        wbytes = lib().dml_ood_partition_workspace_bytes(G)
+        scratch = self.ws.get("d_part_ws", wbytes)
+        b = inner_bounds.to(self.device).contiguous()
+        with torch.cuda.device(self.device):
+            check(lib().dml_ood_partition(ptr(keys), n, ptr(b) if G > 1 else None, G, ptr(out), ptr(counts), ptr(scratch),
+                                          scratch.numel(), stream_ptr(self.device)), "dml_ood_partition")
+        return out, counts
+
 
 def _as_unsigned(t: torch.Tensor) -> torch.Tensor:
     """int32 bit patterns -> int64 values in [0, 2^32) (host-side ordering of a handful of samples)"""
@@ -134,24 +162,28 @@ def choose_splitters(all_samples: torch.Tensor, world: int) -> torch.Tensor:
 
 
 def pooled_measures(conf: torch.Tensor, gt: torch.Tensor, out_labels: Sequence[int] = (13,), *, group=None,
-                    recall_level: float = ood.RECALL_LEVEL_DEFAULT, mode: str = "alltoall", ops=None,
+                    recall_level: float = ood.RECALL_LEVEL_DEFAULT, mode: str = "partition", ops=None,
                     workspace: Optional[ood.OodWorkspace] = None, key_base: int = ood.KEY_BASE_NONNEG):
     """Exact pooled (auroc, aupr, fpr, info) over the (conf, gt) pairs of ALL ranks of ``group``.
     ``conf`` must be non-negative (normalised maps); positives are gt in ``out_labels``; the ranked
     score is -conf like anomaly/eval_ood_traditional.py:139-141.  Collective: every rank must call it."""
-    if mode not in ("alltoall", "allgather"):
-        raise ValueError("mode must be 'alltoall' or 'allgather'")
+    if mode not in ("partition", "alltoall", "allgather"):
+        raise ValueError("mode must be 'partition', 'alltoall' or 'allgather'")
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     ops = ops or CudaOps(conf.device, workspace)
     dev = conf.device
 
     keys, stats = ops.make_keys(conf, gt, out_labels, key_base)
-    srt = ops.sort(keys, "local")
-    n_local = srt.numel()
-
-    # ---- splitters from a regular sample of every sorted shard -----------------------------------
-    smp = ops.sample(srt, SAMPLES_PER_RANK)
+    partition = mode == "partition"
+    n_local = keys.numel()
+    # ---- splitters from a sample of every shard (regular sample of the sorted shard, or a strided sample of
+    #      the unsorted one): ranges are balanced up to sampling error, correctness never depends on them --------
+    if partition:
+        smp = ops.sample_unsorted(keys, PARTITION_SAMPLES_PER_RANK)
+    else:
+        srt = ops.sort(keys, "local")
+        smp = ops.sample(srt, SAMPLES_PER_RANK)
     gathered = [torch.empty_like(smp) for _ in range(world)]
     dist.all_gather(gathered, smp, group=group)
     all_s = torch.cat(gathered).cpu()
@@ -161,9 +193,13 @@ def pooled_measures(conf: torch.Tensor, gt: torch.Tensor, out_labels: Sequence[i
     bounds = choose_splitters(vals, world)                       # int64 [world+1]
     q = (bounds[:-1] & 0xFFFFFFFF).to(torch.int64)
     queries = torch.where(q >= (1 << 31), q - (1 << 32), q).to(torch.int32)   # bit patterns
-    cuts = ops.lower_bound(srt, queries)                          # [world] start of every range in my shard
-    cuts = torch.cat([cuts.cpu(), torch.tensor([n_local])])
-    send_counts = (cuts[1:] - cuts[:-1]).tolist()
+    if partition:
+        srt, cnt_dev = ops.partition(keys, queries[1:])           # grouped by range, not sorted
+        send_counts = cnt_dev.cpu().tolist()
+    else:
+        cuts = ops.lower_bound(srt, queries)                      # [world] start of every range in my shard
+        cuts = torch.cat([cuts.cpu(), torch.tensor([n_local])])
+        send_counts = (cuts[1:] - cuts[:-1]).tolist()
 
     # totals + stats (n_pos, n_nan, n_oow) in one tiny all_reduce
     tot = torch.cat([stats[:3].to(torch.int64), torch.tensor([n_local], dtype=torch.int64, device=dev)])
@@ -183,7 +219,7 @@ def pooled_measures(conf: torch.Tensor, gt: torch.Tensor, out_labels: Sequence[i
     m = int(sum(recv_counts))
     mine = ops.empty_keys(m, "range")
     moved_bytes = 0
-    if mode == "alltoall":
+    if mode in ("alltoall", "partition"):
         dist.all_to_all_single(mine, srt, recv_counts, send_counts, group=group)
         moved_bytes = 4 * (m - recv_counts[rank])
     else:

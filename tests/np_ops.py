@@ -84,5 +84,15 @@ class NumpyOps:
             out[8] = len(ends)
         return torch.from_numpy(out)
 
+    def sample_unsorted(self, keys, n_samples):
+        return self.sample(keys, n_samples)
+
+    def partition(self, keys, inner_bounds):
+        k = _u(keys)
+        b = np.searchsorted(_u(inner_bounds.contiguous()), k, side="right") if inner_bounds.numel() else np.zeros(k.size, np.int64)
+        order = np.argsort(b, kind="stable")
+        counts = np.bincount(b, minlength=inner_bounds.numel() + 1).astype(np.int64)
+        return torch.from_numpy(k[order].view(np.int32).copy()), torch.from_numpy(counts)
+
     def empty_keys(self, n, tag):
         return torch.empty(n, dtype=torch.int32)

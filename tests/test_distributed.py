@@ -56,7 +56,9 @@ def _worker(rank, world, port, case, mode, q):
 
 
 @pytest.mark.parametrize("world,case,mode", [(2, "plain", "alltoall"), (2, "ties", "alltoall"), (2, "ties", "allgather"),
-                                             (3, "skewed", "alltoall"), (3, "empty_rank", "allgather"), (2, "empty_rank", "alltoall")])
+                                             (3, "skewed", "alltoall"), (3, "empty_rank", "allgather"), (2, "empty_rank", "alltoall"),
+                                             (2, "plain", "partition"), (2, "ties", "partition"), (3, "skewed", "partition"),
+                                             (3, "empty_rank", "partition")])
 def test_pooled_measures_gloo(world, case, mode):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()

@@ -47,7 +47,7 @@ def _worker(rank, world, port, mode, q):
 
 
 @pytest.mark.parametrize("world", [1, 2])
-@pytest.mark.parametrize("mode", ["alltoall", "allgather"])
+@pytest.mark.parametrize("mode", ["partition", "alltoall", "allgather"])
 def test_pooled_measures_nccl(world, mode):
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
@@ -69,3 +69,26 @@ def test_pooled_measures_nccl(world, mode):
         assert (r[1], r[2], r[3]) == (results[0][1], results[0][2], results[0][3])
         np.testing.assert_allclose([r[1], r[2], r[3]], ref, rtol=0, atol=1e-12)
         assert r[4]["n_groups"] == np.unique(conf).size
+
+
+@pytest.mark.parametrize("n,n_buckets", [(0, 3), (1, 2), (4095, 1), (4097, 2), (100_003, 8), (1_000_000, 16), (300_000, 5)])
+def test_partition_kernel(n, n_buckets):
+    """dml_ood_partition: exact bucket sizes, every bucket holds exactly its key range (as a multiset)"""
+    from dml_b200.distributed import CudaOps
+    rng = np.random.default_rng(n + n_buckets)
+    keys = rng.integers(0, 1 << 32, n, dtype=np.uint64).astype(np.uint32)
+    if n > 10:
+        keys[: n // 3] = keys[n // 2]                         # a heavy tie
+    inner = np.sort(rng.integers(0, 1 << 32, n_buckets - 1, dtype=np.uint64).astype(np.uint32)) & ~np.uint32(1)
+    if n_buckets > 3:
+        inner[2] = inner[1]                                   # an empty range
+    ops = CudaOps(torch.device("cuda", 0))
+    out, counts = ops.partition(torch.from_numpy(keys.view(np.int32)).cuda(), torch.from_numpy(inner.view(np.int32).copy()))
+    out = out.cpu().numpy().view(np.uint32)
+    counts = counts.cpu().numpy()
+    b = np.searchsorted(inner, keys, side="right")
+    np.testing.assert_array_equal(counts, np.bincount(b, minlength=n_buckets))
+    off = 0
+    for g in range(n_buckets):
+        np.testing.assert_array_equal(np.sort(out[off: off + counts[g]]), np.sort(keys[b == g]))
+        off += counts[g]
