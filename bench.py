@@ -278,6 +278,8 @@ class Pipeline:
             self.outs.append(H.HeadOutput(label=self.label[s:e], eds=self.eds[s:e], msp=self.msp[s:e],
                                           minmax=self.minmax[s:e], confusion=self.confusion))
         self.head_events = []
+        self.metric_events = []
+        self.pooled_events = []
         self.pooled_result = None
 
     # one chunk: head -> finalize (MMSP + mix maps) -> fused-normalisation key-gen + per-image metrics
@@ -293,11 +295,16 @@ class Pipeline:
             ev1.record()
             self.head_events.append((ev0, ev1))
         nb = e - s
+        if time_head:
+            ev2 = torch.cuda.Event(enable_timing=True)
         # key-gen reads the raw EDS once: normalised conf map, MMSP map, mix map and ranking keys
         res, stats = ood.eval_segments(self.eds[s:e], nb, self.hw, gt=gt, out_labels=(self.k,), score_kind=0,
                                        minmax=self.minmax[s:e], minmax_slot=0, conf_out=self.conf[s:e],
                                        workspace=self.ws_img, msp=self.msp[s:e], msp_norm_out=self.mmsp_c[:nb],
                                        mix_out=self.mix_c[:nb])
+        if time_head:
+            ev2.record()
+            self.metric_events.append((ev1, ev2))
         self.per_image[s:e].copy_(res)
         self.per_image_stats[s:e].copy_(stats)
 
@@ -316,7 +323,13 @@ class Pipeline:
         self.confusion.zero_()
         for ci, (s, e) in enumerate(self.bounds):
             self.process_chunk(ci, x_all[s:e], gt_all[s:e], time_head)
+        if time_head:
+            p0, p1 = self.torch.cuda.Event(enable_timing=True), self.torch.cuda.Event(enable_timing=True)
+            p0.record()
         self.pooled(gt_all)
+        if time_head:
+            p1.record()
+            self.pooled_events.append((p0, p1))
 
 
 def run_ours(args):
@@ -363,6 +376,8 @@ def run_ours(args):
         pipe.step_resident(x_all, gt_all)
     barrier()
     pipe.head_events.clear()
+    pipe.metric_events.clear()
+    pipe.pooled_events.clear()
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
@@ -410,6 +425,28 @@ def run_ours(args):
                 "peak_source": peak_src, "bytes_per_pixel": head_bpp, "avg_launch_ms": head_ms_avg,
                 "head_share_of_step": sum(head_ms) / (ms_total if ms_total > 0 else 1.0)}
 
+    # the other stages of the step, from the same CUDA-event timeline (traffic MODELS, stated per pair):
+    #   per-image metrics: key-gen (read eds 4 + msp 4 + gt 1, write conf 4 + mmsp 4 + mix 4 + key 4) + digit histograms
+    #   (read 4) + 4 radix passes (read 4 + write 4) + tie-aware scan (2 reads of 4) = 69 B / pair
+    #   pooled metrics (1 GPU): key-gen (read conf 4 + gt 1, write key 4) + hist 4 + 4 x 8 + scan 8 = 53 B / pair
+    met_ms = [a.elapsed_time(b) for a, b in pipe.metric_events]
+    pool_ms = [a.elapsed_time(b) for a, b in pipe.pooled_events]
+    stages = [{"stage": "head (dominant streaming kernel, roofline above)", "ms_per_step": sum(head_ms) / args.steps,
+               "share_of_step": sum(head_ms) / ms_total}]
+    if met_ms:
+        gbs = tot_px * 69 / (sum(met_ms) * 1e-3) / 1e9
+        stages.append({"stage": "per-image exact metrics: key-gen + segmented radix sort (4 x 8 bit) + tie-aware scan",
+                       "ms_per_step": sum(met_ms) / args.steps, "share_of_step": sum(met_ms) / ms_total,
+                       "bytes_per_pair_model": 69, "achieved_GBps": gbs, "frac_of_hbm_peak": gbs / peak,
+                       "Gpairs_per_s": tot_px / (sum(met_ms) * 1e-3) / 1e9})
+    if pool_ms and not args.no_pooled:
+        stages.append({"stage": "pooled exact metrics over all pairs of the step" + (" (local part + NCCL exchange)" if world > 1 else ""),
+                       "ms_per_step": sum(pool_ms) / args.steps, "share_of_step": sum(pool_ms) / ms_total,
+                       "bytes_per_pair_model": 53 if world == 1 else None,
+                       "achieved_GBps": (tot_px * 53 / (sum(pool_ms) * 1e-3) / 1e9) if world == 1 else None,
+                       "Gpairs_per_s": tot_px / (sum(pool_ms) * 1e-3) / 1e9})
+    roofline["stages"] = stages
+
     # ---- results (also the parity self-check of the bench) ------------------------------------------
     vals, counts = pipe.ood.results_to_host(pipe.per_image, pipe.per_image_stats)
     ok = ~np.isnan(vals[:, 0])
@@ -453,7 +490,8 @@ def run_ours(args):
                 "data": "synthetic",
                 "config": {"workload": workload_name(args), "images_per_gpu": n, "chunk_images": pipe.chunk,
                            "l2": "inputs (%.1f GB/step/GPU) far exceed the 126 MB L2; no flush needed" % (n * k * hw * 4 / 1e9),
-                           "pooled": "single GPU sort" if world == 1 else "range-partitioned NCCL exchange of locally sorted shards"},
+                           "pooled": "single GPU sort" if world == 1 else
+                           "range partition of the unsorted keys + NCCL all-to-all + one local sort per rank (mode=partition)"},
                 "roofline": roofline, "cpu_baseline": cpu,
                 "e2e": ({"value": e2e["value"], "unit": UNIT, "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
                          "ms_per_step": e2e["ms_per_step"], "steps": e2e["steps"], "note": e2e["note"]} if e2e else None),
