@@ -355,17 +355,28 @@ __device__ __forceinline__ CarryH carryh_combine(const CarryH& a, const CarryH& 
   r.head = a.head | b.head;
   return r;
 }
+// One CTA handles `per_chunk` consecutive tiles of a segment (chunks == 1: the whole segment, the per-image case).
+// Long segments (the pooled metric: > 300 000 tiles) are split into chunks so that the scan is not serialised on one
+// SM: PHASE 1 writes each chunk's total, scan_chunk_prefix_kernel turns the totals into exclusive chunk prefixes, and
+// PHASE 2 redoes the in-chunk scan starting from its prefix.  PHASE 0 = single level (prefix = the range's carry-in).
+template <int PHASE>
 __global__ void __launch_bounds__(CARRY_THREADS) scan_carry_kernel(const Agg* __restrict__ tile_agg, int tiles_per_seg,
+                                                                   int per_chunk, int chunks,
                                                                    const RangeInfo* __restrict__ info,
+                                                                   CarryH* __restrict__ chunk_state,
                                                                    Carry* __restrict__ tile_carry) {
   __shared__ CarryH s_t[CARRY_THREADS];
-  const int seg = blockIdx.x, tid = threadIdx.x;
+  const int seg = blockIdx.x / chunks, chunk = blockIdx.x - seg * chunks, tid = threadIdx.x;
   const Agg* ag = tile_agg + (size_t)seg * tiles_per_seg;
   Carry* out = tile_carry + (size_t)seg * tiles_per_seg;
-  const int per = (tiles_per_seg + CARRY_THREADS - 1) / CARRY_THREADS;
-  const int b = tid * per;
+  const int t0 = chunk * per_chunk;
+  int t1 = t0 + per_chunk;
+  if (t1 > tiles_per_seg) t1 = tiles_per_seg;
+  const int per = (t1 - t0 + CARRY_THREADS - 1) / CARRY_THREADS;
+  int b = t0 + tid * per;
+  if (b > t1) b = t1;
   int e = b + per;
-  if (e > tiles_per_seg) e = tiles_per_seg;
+  if (e > t1) e = t1;
   CarryH mine;
   mine.c.pos = mine.c.spos = mine.c.slen = 0ull;
   mine.head = 0;
@@ -380,15 +391,49 @@ __global__ void __launch_bounds__(CARRY_THREADS) scan_carry_kernel(const Agg* __
     s_t[tid] = v;
     __syncthreads();
   }
+  if (PHASE == 1) {
+    if (tid == CARRY_THREADS - 1) chunk_state[blockIdx.x] = s_t[tid];
+    return;
+  }
   CarryH run;
-  run.c.pos = (unsigned long long)info[seg].pos_before;  // the range starts on a group boundary
-  run.c.spos = run.c.slen = 0ull;
-  run.head = 0;
+  if (PHASE == 2) {
+    run = chunk_state[blockIdx.x];
+  } else {
+    run.c.pos = (unsigned long long)info[seg].pos_before;  // the range starts on a group boundary
+    run.c.spos = run.c.slen = 0ull;
+    run.head = 0;
+  }
   if (tid > 0) run = carryh_combine(run, s_t[tid - 1]);
   for (int i = b; i < e; ++i) {
     out[i] = run.c;
     carry_apply(run.c, run.head, ag[i]);
   }
+}
+
+// chunk totals -> exclusive chunk prefixes (in place), one CTA per segment, chunks <= CARRY_THREADS
+__global__ void __launch_bounds__(CARRY_THREADS) scan_chunk_prefix_kernel(CarryH* __restrict__ chunk_state, int chunks,
+                                                                          const RangeInfo* __restrict__ info) {
+  __shared__ CarryH s_t[CARRY_THREADS];
+  const int seg = blockIdx.x, tid = threadIdx.x;
+  CarryH mine;
+  mine.c.pos = mine.c.spos = mine.c.slen = 0ull;
+  mine.head = 0;
+  if (tid < chunks) mine = chunk_state[(size_t)seg * chunks + tid];
+  s_t[tid] = mine;
+  __syncthreads();
+  for (int o = 1; o < CARRY_THREADS; o <<= 1) {
+    CarryH v = s_t[tid];
+    if (tid >= o) v = carryh_combine(s_t[tid - o], v);
+    __syncthreads();
+    s_t[tid] = v;
+    __syncthreads();
+  }
+  CarryH run;
+  run.c.pos = (unsigned long long)info[seg].pos_before;
+  run.c.spos = run.c.slen = 0ull;
+  run.head = 0;
+  if (tid > 0) run = carryh_combine(run, s_t[tid - 1]);
+  if (tid < chunks) chunk_state[(size_t)seg * chunks + tid] = run;
 }
 
 // phase 3: per-tile group contributions
@@ -523,21 +568,28 @@ __global__ void __launch_bounds__(SCAN_THREADS, 3) scan_apply_kernel(const uint3
 
 // phase 4: fixed-order reduction of the tile partials of each segment
 constexpr int FIN_THREADS = 256;
+// `chunks` > 1: block (seg, chunk) merges tiles [chunk*per_chunk, ...) of its segment into range_partials[seg*chunks + chunk]
+// (first level of the two-level reduction of long segments); chunks == 1: whole segment.
 __global__ void __launch_bounds__(FIN_THREADS) scan_finalize_kernel(const TilePartial* __restrict__ partials, int tiles_per_seg,
+                                                                    int per_chunk, int chunks,
                                                                     const RangeInfo* __restrict__ info,
                                                                     const unsigned long long* __restrict__ seg_stats,
                                                                     double recall_level, dml_ood_result* __restrict__ results,
                                                                     TilePartial* __restrict__ range_partials) {
   __shared__ TilePartial s_t[FIN_THREADS];
-  const int seg = blockIdx.x, tid = threadIdx.x;
+  const int seg = blockIdx.x / chunks, chunk = blockIdx.x - seg * chunks, tid = threadIdx.x;
   const TilePartial* pp = partials + (size_t)seg * tiles_per_seg;
   TilePartial t;
   partial_init(t);
   // contiguous chunk per thread => the same summation order regardless of scheduling
-  const int per = (tiles_per_seg + FIN_THREADS - 1) / FIN_THREADS;
-  const int b = tid * per;
+  const int t0 = chunk * per_chunk;
+  int t1 = t0 + per_chunk;
+  if (t1 > tiles_per_seg) t1 = tiles_per_seg;
+  const int per = (t1 - t0 + FIN_THREADS - 1) / FIN_THREADS;
+  int b = t0 + tid * per;
+  if (b > t1) b = t1;
   int e = b + per;
-  if (e > tiles_per_seg) e = tiles_per_seg;
+  if (e > t1) e = t1;
   for (int i = b; i < e; ++i) partial_merge(t, pp[i]);
   s_t[tid] = t;
   __syncthreads();
@@ -551,7 +603,7 @@ __global__ void __launch_bounds__(FIN_THREADS) scan_finalize_kernel(const TilePa
   }
   if (tid == 0) {
     const TilePartial r = s_t[0];
-    if (range_partials) range_partials[seg] = r;
+    if (range_partials) range_partials[blockIdx.x] = r;
     if (results) {
       const RangeInfo ri = info[seg];
       const double P = (double)ri.total_pos, N = (double)(ri.total_n - ri.total_pos);
@@ -612,10 +664,13 @@ __global__ void range_info_from_stats_kernel(const unsigned long long* __restric
   }
 }
 
+constexpr int SCAN_CHUNK_TILES = 2048;       // tiles per chunk of the two-level carry / finalize (long segments only)
+constexpr int SCAN_CHUNK_MIN_TILES = 8192;   // segments shorter than this stay single-level
 struct MetricsPlan {
   SortPlan sort;
   int tiles_per_seg;  // scan tiles
-  size_t off_agg, off_carry, off_partial, off_info, off_end;
+  int chunks;         // > 1: two-level carry / finalize
+  size_t off_agg, off_carry, off_partial, off_info, off_chunk_state, off_chunk_partial, off_end;
 };
 
 MetricsPlan make_metrics_plan(int n_seg, long long seg_len) {
@@ -629,7 +684,14 @@ MetricsPlan make_metrics_plan(int n_seg, long long seg_len) {
   m.off_carry = align(m.off_agg + nt * sizeof(Agg));
   m.off_partial = align(m.off_carry + nt * sizeof(Carry));
   m.off_info = align(m.off_partial + nt * sizeof(TilePartial));
-  m.off_end = align(m.off_info + (size_t)n_seg * sizeof(RangeInfo));
+  m.chunks = 1;
+  if (m.tiles_per_seg >= SCAN_CHUNK_MIN_TILES) {
+    m.chunks = (m.tiles_per_seg + SCAN_CHUNK_TILES - 1) / SCAN_CHUNK_TILES;
+    if (m.chunks > CARRY_THREADS) m.chunks = 1;   // > 8.6 G keys per segment: not reachable (seg_len < 2^32)
+  }
+  m.off_chunk_state = align(m.off_info + (size_t)n_seg * sizeof(RangeInfo));
+  m.off_chunk_partial = align(m.off_chunk_state + (size_t)n_seg * m.chunks * sizeof(CarryH));
+  m.off_end = align(m.off_chunk_partial + (size_t)n_seg * m.chunks * sizeof(TilePartial));
   return m;
 }
 
@@ -641,12 +703,31 @@ int run_scan(const uint32_t* sorted, const MetricsPlan& m, unsigned char* ws, co
   dim3 grid((unsigned)m.tiles_per_seg, (unsigned)m.sort.n_seg);
   scan_agg_kernel<<<grid, SCAN_THREADS, 0, stream>>>(sorted, m.sort.seg_len, m.tiles_per_seg, agg);
   DML_LAUNCH_CHECK();
-  scan_carry_kernel<<<m.sort.n_seg, CARRY_THREADS, 0, stream>>>(agg, m.tiles_per_seg, info, carry);
-  DML_LAUNCH_CHECK();
+  CarryH* chunk_state = reinterpret_cast<CarryH*>(ws + m.off_chunk_state);
+  TilePartial* chunk_partial = reinterpret_cast<TilePartial*>(ws + m.off_chunk_partial);
+  if (m.chunks > 1) {
+    scan_carry_kernel<1><<<m.sort.n_seg * m.chunks, CARRY_THREADS, 0, stream>>>(agg, m.tiles_per_seg, SCAN_CHUNK_TILES, m.chunks, info, chunk_state, carry);
+    DML_LAUNCH_CHECK();
+    scan_chunk_prefix_kernel<<<m.sort.n_seg, CARRY_THREADS, 0, stream>>>(chunk_state, m.chunks, info);
+    DML_LAUNCH_CHECK();
+    scan_carry_kernel<2><<<m.sort.n_seg * m.chunks, CARRY_THREADS, 0, stream>>>(agg, m.tiles_per_seg, SCAN_CHUNK_TILES, m.chunks, info, chunk_state, carry);
+    DML_LAUNCH_CHECK();
+  } else {
+    scan_carry_kernel<0><<<m.sort.n_seg, CARRY_THREADS, 0, stream>>>(agg, m.tiles_per_seg, m.tiles_per_seg, 1, info, chunk_state, carry);
+    DML_LAUNCH_CHECK();
+  }
   scan_apply_kernel<<<grid, SCAN_THREADS, 0, stream>>>(sorted, m.sort.seg_len, m.tiles_per_seg, carry, info, recall_level, partial);
   DML_LAUNCH_CHECK();
-  scan_finalize_kernel<<<m.sort.n_seg, FIN_THREADS, 0, stream>>>(partial, m.tiles_per_seg, info, seg_stats, recall_level, results, range_partials);
-  DML_LAUNCH_CHECK();
+  if (m.chunks > 1) {
+    // level 1: chunk partials (fixed order inside a chunk); level 2: the chunk partials of each segment
+    scan_finalize_kernel<<<m.sort.n_seg * m.chunks, FIN_THREADS, 0, stream>>>(partial, m.tiles_per_seg, SCAN_CHUNK_TILES, m.chunks, info, nullptr, recall_level, nullptr, chunk_partial);
+    DML_LAUNCH_CHECK();
+    scan_finalize_kernel<<<m.sort.n_seg, FIN_THREADS, 0, stream>>>(chunk_partial, m.chunks, m.chunks, 1, info, seg_stats, recall_level, results, range_partials);
+    DML_LAUNCH_CHECK();
+  } else {
+    scan_finalize_kernel<<<m.sort.n_seg, FIN_THREADS, 0, stream>>>(partial, m.tiles_per_seg, m.tiles_per_seg, 1, info, seg_stats, recall_level, results, range_partials);
+    DML_LAUNCH_CHECK();
+  }
   return DML_OK;
 }
 

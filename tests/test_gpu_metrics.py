@@ -118,3 +118,24 @@ def test_large_single_segment_properties():
     a3, _, _ = ood.measures_from_scores(-score, ~pos)
     assert abs(a3 - a1) < 1e-12
     assert 0.5 < a1 < 1 and 0 < p1 < 1 and 0 < f1 <= 1
+
+
+def test_long_segment_two_level_scan_matches_oracle():
+    """40 M pairs in ONE segment (> 8192 scan tiles: the chunked two-level carry / finalize path of the pooled
+    metric) against the CPU oracle, including a run of equal keys that spans several chunks."""
+    from dml_b200 import ood
+    n = 40_000_003
+    g = torch.Generator(device="cuda").manual_seed(11)
+    score = torch.rand(n, device="cuda", generator=g)
+    score[::7] = (score[::7] * 512).round() / 512          # heavy ties
+    score[::13] = 1.0                                       # a plateau spanning many tiles
+    pos = torch.rand(n, device="cuda", generator=g) < (0.02 + 0.05 * score)
+    a, p, f = ood.measures_from_scores(score, pos)
+    ref = O.get_measures(score[pos].cpu().numpy(), score[~pos].cpu().numpy())
+    np.testing.assert_allclose([a, p, f], ref, rtol=0, atol=1e-9)
+    # a block of equal keys longer than a whole chunk (2048 tiles = 8.4 M keys) must carry across chunk borders
+    score2 = score.clone()
+    score2[5_000_000:25_000_000] = 0.5
+    a2, p2, f2 = ood.measures_from_scores(score2, pos)
+    ref2 = O.get_measures(score2[pos].cpu().numpy(), score2[~pos].cpu().numpy())
+    np.testing.assert_allclose([a2, p2, f2], ref2, rtol=0, atol=1e-9)
