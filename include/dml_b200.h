@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define DML_B200_ABI_VERSION 1
+#define DML_B200_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define DML_API __attribute__((visibility("default")))
@@ -249,20 +249,36 @@ DML_API int dml_ood_keystats(const float* values, int32_t score_kind, int32_t n_
  * seg_stats (device, [n_seg,4] int64) = (n_pos, n_nan, n_out_of_window, 0).
  * Optional fused score outputs (need minmax, minmax_slot == 0): with `msp` = raw max-softmax map,
  * `msp_norm_out` = its min-max normalisation (MMSP, eval_ood_traditional.py:434-435) and `mix_out` =
- * c*eds_n + (1-c)*mmsp with c = 1/(1+exp(lambda (eds_n - thr))) (:104-106,447-448). */
+ * c*eds_n + (1-c)*mmsp with c = 1/(1+exp(lambda (eds_n - thr))) (:104-106,447-448).
+ * `sort_workspace` != NULL (the workspace later passed to dml_ood_eval_segments for the same n_seg / seg_len):
+ * the digit histograms of all radix passes are accumulated here, while the keys are still in registers, and
+ * dml_ood_eval_segments is then called with hist_precomputed = 1 (the sort's separate counting read of the
+ * keys disappears; key-gen is HBM-bound, the histogram shared-atomic-bound, so the two overlap). */
 DML_API int dml_ood_keygen(const float* values, const float* minmax, int32_t minmax_slot, float* conf_out,
                    const uint8_t* gt_u8, const int64_t* gt_i64, uint64_t out_label_mask,
                    const uint8_t* pos_u8, int32_t score_kind, uint32_t key_base, int32_t n_seg,
                    int64_t seg_len, uint32_t* keys, long long* seg_stats, const float* msp,
-                   float* msp_norm_out, float* mix_out, float lambda, float thr, dml_stream_t stream);
+                   float* msp_norm_out, float* mix_out, float lambda, float thr, void* sort_workspace,
+                   size_t sort_workspace_bytes, dml_stream_t stream);
 
 DML_API size_t dml_ood_workspace_bytes(int32_t n_seg, int64_t seg_len);
 /* Sort `keys` (n_seg segments of seg_len packed keys; clobbered) and evaluate every segment.
  * `seg_stats` is dml_ood_keygen's output (n_pos / n_nan per segment, device).
+ * `hist_precomputed` != 0: dml_ood_keygen already left the digit histograms in `workspace`.
  * `results` is a DEVICE array of n_seg dml_ood_result.  recall_level: 0.95 in the reference. */
 DML_API int dml_ood_eval_segments(uint32_t* keys, const long long* seg_stats, int32_t n_seg, int64_t seg_len,
-                          double recall_level, void* workspace, size_t workspace_bytes,
+                          double recall_level, void* workspace, size_t workspace_bytes, int32_t hist_precomputed,
                           dml_ood_result* results, dml_stream_t stream);
+
+/* Second FPR@recall convention, used by the reference's softmax-baseline evaluator
+ * (DeepLabV3Plus-Pytorch/test.py:241-244): fpr[tpr >= recall_level][0] on
+ * sklearn.metrics.roc_curve(y, score) with its default drop_intermediate=True, i.e. the FIRST kept ROC point
+ * whose recall reaches the level (dml_ood_result.fpr is the closest-recall rule of anomaly/anom_utils.py:57-65).
+ * Call right after dml_ood_eval_segments with the same keys / seg_stats / workspace (it reads the sorted keys
+ * and the per-tile carries the scan left there).  fpr_out: DEVICE [n_seg] float64, NaN for single-class segments. */
+DML_API int dml_ood_roc_fpr(const uint32_t* keys, const long long* seg_stats, int32_t n_seg, int64_t seg_len,
+                    double recall_level, const void* workspace, size_t workspace_bytes, double* fpr_out,
+                    dml_stream_t stream);
 
 /* Building blocks for the multi-GPU pooled metric (locally sorted shards + NCCL exchange on the
  * Python side).  dml_ood_sort: radix sort only, bits [begin_bit, end_bit); `*sorted_out` (host

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libdml_b200.so")
 
 DML_OK = 0
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 c_f32p = C.c_void_p
 c_void_p = C.c_void_p
@@ -93,10 +93,13 @@ SIGNATURES = {
     "dml_ood_keystats": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p]),
     "dml_ood_keygen": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64,
                                  C.c_void_p, C.c_int32, C.c_uint32, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p,
-                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p]),
+                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_size_t,
+                                 C.c_void_p]),
     "dml_ood_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int64]),
     "dml_ood_eval_segments": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_double, C.c_void_p,
-                                        C.c_size_t, C.c_void_p, C.c_void_p]),
+                                        C.c_size_t, C.c_int32, C.c_void_p, C.c_void_p]),
+    "dml_ood_roc_fpr": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_double, C.c_void_p, C.c_size_t,
+                                  C.c_void_p, C.c_void_p]),
     "dml_ood_sort": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_size_t,
                                C.POINTER(C.c_void_p), C.c_void_p]),
     "dml_ood_partition_workspace_bytes": (C.c_size_t, [C.c_int32]),

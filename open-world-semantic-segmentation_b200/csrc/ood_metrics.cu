@@ -62,12 +62,44 @@ struct KeygenFuse {
   float lambda, thr;
 };
 
-template <typename GT, int VEC>
+struct HistArgs {
+  uint32_t* ghist;   // [n_seg][MAX_PASSES][RADIX] inside the sort workspace (zeroed by the caller)
+  int n_passes;
+  int shifts[MAX_PASSES];
+};
+__device__ __forceinline__ unsigned lanemask_lt_() {
+  unsigned m;
+  asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+  return m;
+}
+// lanes of the warp holding the same 8-bit digit (8 ballots); every lane of the warp must call it
+__device__ __forceinline__ unsigned match8_ballot(uint32_t d) {
+  unsigned peers = 0xffffffffu;
+#pragma unroll
+  for (int b = 0; b < RADIX_BITS; ++b) {
+    const bool bit = (d >> b) & 1u;
+    const unsigned vote = __ballot_sync(0xffffffffu, bit);
+    peers &= bit ? vote : ~vote;
+  }
+  return peers;
+}
+// HIST: the digit histograms of all radix passes (the sort's up-front counting read) are accumulated here, while
+// the keys are still in registers: key-gen is HBM-bound and the histogram is shared-atomic-bound, so the two overlap
+// and the sort's separate 4 B/key histogram pass (hist_kernel) disappears.  Same scheme as hist_kernel: warp-private
+// shared histograms, plain shared atomics for the (near-uniform) lower digit places, ballot-grouped adds for the
+// heavily skewed top place.
+template <typename GT, int VEC, bool HIST>
 __global__ void __launch_bounds__(256) keygen_kernel(const float* __restrict__ values, const float* __restrict__ minmax,
                                                      int slot, float* conf_out, const GT* __restrict__ gt,
                                                      uint64_t out_mask, const uint8_t* __restrict__ pos_u8, int kind,
                                                      long long seg_len, uint32_t key_base, uint32_t* __restrict__ keys,
-                                                     unsigned long long* seg_stats, const KeygenFuse fz) {
+                                                     unsigned long long* seg_stats, const KeygenFuse fz,
+                                                     const HistArgs hz) {
+  __shared__ uint32_t s_h[HIST ? SORT_WARPS : 1][HIST ? MAX_PASSES : 1][HIST ? RADIX : 1];
+  if constexpr (HIST) {
+    for (int i = threadIdx.x; i < SORT_WARPS * MAX_PASSES * RADIX; i += 256) (&s_h[0][0][0])[i] = 0u;
+    __syncthreads();
+  }
   const int seg = blockIdx.y;
   const size_t base = (size_t)seg * (size_t)seg_len;
   float lo = 0.f, den = 1.f, mlo = 0.f, mden = 1.f;
@@ -81,8 +113,14 @@ __global__ void __launch_bounds__(256) keygen_kernel(const float* __restrict__ v
   const bool fuse = fz.msp != nullptr;
   unsigned n_pos = 0, n_nan = 0, n_oow = 0;
   const long long nvec = seg_len / VEC;
-  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < nvec; q += (long long)gridDim.x * blockDim.x) {
-    const size_t i = base + (size_t)q * VEC;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  // HIST needs warp-uniform trip counts (ballots): iterate to the block-uniform bound and mask the tail
+  const long long q_end = HIST ? ((nvec + stride - 1) / stride) * stride : nvec;
+  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < q_end; q += stride) {
+    // a lane past the end re-reads the segment's last vector with every side effect masked, so that the whole warp
+    // executes the same top-place ballots
+    const bool live = !HIST || q < nvec;
+    const size_t i = base + (size_t)(live ? q : nvec - 1) * VEC;
     float v[VEC];
     bool pos[VEC];
     if constexpr (VEC == 4) {
@@ -106,8 +144,9 @@ __global__ void __launch_bounds__(256) keygen_kernel(const float* __restrict__ v
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
       if (norm) v[j] = __fdiv_rn(__fsub_rn(v[j], lo), den);  // NumPy: (x - min) / (max - min), fp32
-      n_pos += pos[j];
-      key[j] = pack_key(v[j], kind, pos[j], key_base, n_nan, n_oow);
+      unsigned c_nan = 0, c_oow = 0;
+      key[j] = pack_key(v[j], kind, pos[j], key_base, c_nan, c_oow);
+      if (live) { n_pos += pos[j]; n_nan += c_nan; n_oow += c_oow; }
     }
     if (fuse) {
       float m[VEC];
@@ -125,6 +164,28 @@ __global__ void __launch_bounds__(256) keygen_kernel(const float* __restrict__ v
         mx[j] = __fadd_rn(__fmul_rn(c, v[j]), __fmul_rn(__fsub_rn(1.0f, c), mn[j]));
       }
     }
+    if constexpr (HIST) {
+      const int w = threadIdx.x >> 5;
+      const unsigned lt = lanemask_lt_();
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) {
+#pragma unroll
+        for (int p = 0; p < MAX_PASSES; ++p) {
+          if (p < hz.n_passes) {
+            const uint32_t d = (key[j] >> hz.shifts[p]) & (RADIX - 1);
+            if (p < hz.n_passes - 1) {
+              if (live) atomicAdd(&s_h[w][p][d], 1u);
+            } else {
+              const unsigned vm = __ballot_sync(0xffffffffu, live);
+              const unsigned peers = match8_ballot(d) & vm;
+              if (live && (peers & lt) == 0u) s_h[w][p][d] += (uint32_t)__popc(peers);
+              __syncwarp();
+            }
+          }
+        }
+      }
+    }
+    if (!live) continue;   // (after the ballots) nothing to store
     if constexpr (VEC == 4) {
       *reinterpret_cast<uint4*>(keys + i) = make_uint4(key[0], key[1], key[2], key[3]);
       if (conf_out) *reinterpret_cast<float4*>(conf_out + i) = make_float4(v[0], v[1], v[2], v[3]);
@@ -135,6 +196,16 @@ __global__ void __launch_bounds__(256) keygen_kernel(const float* __restrict__ v
       if (conf_out) conf_out[i] = v[0];
       if (fuse && fz.msp_norm) fz.msp_norm[i] = mn[0];
       if (fuse && fz.mix) fz.mix[i] = mx[0];
+    }
+  }
+  if constexpr (HIST) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < hz.n_passes * RADIX; i += 256) {
+      const int p = i >> RADIX_BITS, d = i & (RADIX - 1);
+      uint32_t c = 0;
+#pragma unroll
+      for (int ww = 0; ww < SORT_WARPS; ++ww) c += s_h[ww][p][d];
+      if (c) atomicAdd(hz.ghist + ((size_t)seg * MAX_PASSES + p) * RADIX + d, c);
     }
   }
   // block reduce the three counters
@@ -664,6 +735,136 @@ __global__ void range_info_from_stats_kernel(const unsigned long long* __restric
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Second FPR@recall convention: fpr[tpr >= recall][0] on sklearn.metrics.roc_curve(drop_intermediate=True)
+// (the softmax-baseline evaluator, DeepLabV3Plus-Pytorch/test.py:241-244).  Runs after the scan on the same
+// workspace: the per-tile carries locate the tile that holds the T-th positive (T = the smallest count whose
+// float64 recall T/P reaches the level), one block finds the element, and warp 0 then walks the score groups:
+// the ROC point of a group is dropped by roc_curve iff the NEXT group has the same (positives, negatives)
+// counts (both second differences vanish), so the answer is the false-positive count at the end of the run of
+// equal-count groups that starts at the group holding the T-th positive (the first and last points always stay).
+// ---------------------------------------------------------------------------------------------
+struct GroupSpan { long long end; unsigned long long pos; };   // last index of the group, positives in [from, end]
+
+// warp-cooperative: extends the group of `score` (key >> 1) from index `from` (whose score is `score`) to its end
+__device__ __forceinline__ GroupSpan warp_group_end(const uint32_t* __restrict__ k, long long n, long long from, uint32_t score) {
+  const int lane = threadIdx.x & 31;
+  GroupSpan g;
+  g.end = from - 1;
+  g.pos = 0ull;
+  for (long long base = from; base < n; base += 32) {
+    const long long i = base + lane;
+    const uint32_t key = i < n ? k[i] : 0u;
+    const bool same = i < n && (key >> 1) == score;
+    const unsigned m = __ballot_sync(0xffffffffu, same);
+    const int run = m == 0xffffffffu ? 32 : __ffs(~m) - 1;             // leading lanes still inside the group
+    const unsigned in_run = run == 32 ? 0xffffffffu : ((1u << run) - 1u);
+    g.pos += __popc(__ballot_sync(0xffffffffu, same && (key & 1u)) & in_run);
+    g.end += run;
+    if (run < 32) break;
+  }
+  return g;
+}
+// ... and backwards: first index of the group that contains `from`, positives in [start, from)
+__device__ __forceinline__ GroupSpan warp_group_start(const uint32_t* __restrict__ k, long long from, uint32_t score) {
+  const int lane = threadIdx.x & 31;
+  GroupSpan g;
+  g.end = from;   // (re-used as "start")
+  g.pos = 0ull;
+  for (long long base = from - 1; base >= 0; base -= 32) {
+    const long long i = base - lane;
+    const uint32_t key = i >= 0 ? k[i] : 0u;
+    const bool same = i >= 0 && (key >> 1) == score;
+    const unsigned m = __ballot_sync(0xffffffffu, same);
+    const int run = m == 0xffffffffu ? 32 : __ffs(~m) - 1;
+    const unsigned in_run = run == 32 ? 0xffffffffu : ((1u << run) - 1u);
+    g.pos += __popc(__ballot_sync(0xffffffffu, same && (key & 1u)) & in_run);
+    g.end -= run;
+    if (run < 32) break;
+  }
+  return g;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) roc_fpr_kernel(const uint32_t* __restrict__ keys, long long seg_len,
+                                                               int tiles_per_seg, const Carry* __restrict__ tile_carry,
+                                                               const unsigned long long* __restrict__ seg_stats,
+                                                               double recall_level, double* __restrict__ out) {
+  __shared__ unsigned s_warp[SCAN_WARPS];
+  __shared__ long long s_e0;
+  const int seg = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const uint32_t* k = keys + (size_t)seg * (size_t)seg_len;
+  const long long P = (long long)seg_stats[(size_t)seg * 4 + 0];
+  const long long N = seg_len - P;
+  if (P <= 0 || N <= 0) {
+    if (tid == 0) out[seg] = __longlong_as_double(0x7ff8000000000000ll);
+    return;
+  }
+  // T = smallest t in [1, P] with (double)t / P >= recall_level
+  long long T;
+  {
+    const double dP = (double)P;
+    double g = ceil(recall_level * dP);
+    T = g < 1.0 ? 1 : (g > dP ? P : (long long)g);
+    while (T > 1 && (double)(T - 1) / dP >= recall_level) --T;
+    while (T < P && (double)T / dP < recall_level) ++T;
+  }
+  // tile holding the T-th positive: the last tile whose carry (positives before it) is < T
+  const Carry* carry = tile_carry + (size_t)seg * tiles_per_seg;
+  int lo = 0, hi = tiles_per_seg - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if ((long long)carry[mid].pos < T) lo = mid; else hi = mid - 1;
+  }
+  const long long tile_off = (long long)lo * SCAN_TILE;
+  const long long need = T - (long long)carry[lo].pos;            // 1-based rank of the positive inside the tile
+  // blocked positives count per thread, block-wide inclusive scan
+  const long long first = tile_off + (long long)tid * SCAN_ITEMS;
+  unsigned cnt = 0;
+#pragma unroll
+  for (int j = 0; j < SCAN_ITEMS; ++j) cnt += (first + j < seg_len) ? (k[first + j] & 1u) : 0u;
+  unsigned incl = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned nb = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += nb;
+  }
+  if (lane == 31) s_warp[w] = incl;
+  __syncthreads();
+  unsigned before = incl - cnt;
+  for (int i = 0; i < w; ++i) before += s_warp[i];
+  if ((long long)before < need && need <= (long long)(before + cnt)) {
+    unsigned c = before;
+    for (int j = 0; j < SCAN_ITEMS; ++j) {
+      if (first + j < seg_len && (k[first + j] & 1u)) {
+        if ((long long)(++c) == need) { s_e0 = first + j; break; }
+      }
+    }
+  }
+  __syncthreads();
+  if (w != 0) return;
+  // ---- warp 0: the group of the T-th positive, then the run of equal-count groups -------------------
+  const long long e0 = s_e0;
+  const uint32_t score0 = k[e0] >> 1;
+  const GroupSpan fwd = warp_group_end(k, seg_len, e0, score0);              // positives in [e0, end]
+  const GroupSpan bwd = warp_group_start(k, e0, score0);                      // positives in [start, e0)
+  long long end = fwd.end;
+  long long tps = (T - 1) + (long long)fwd.pos;                                // cumulative positives at the group's end
+  long long g_pos = (long long)(fwd.pos + bwd.pos);
+  long long g_neg = (end - bwd.end + 1) - g_pos;
+  const bool is_first_group = bwd.end == 0;
+  if (!is_first_group) {
+    while (end + 1 < seg_len) {
+      const uint32_t sc = k[end + 1] >> 1;
+      const GroupSpan nx = warp_group_end(k, seg_len, end + 1, sc);
+      const long long n_pos = (long long)nx.pos, n_neg = (nx.end - end) - n_pos;
+      if (n_pos != g_pos || n_neg != g_neg) break;                            // this point has a non-zero second difference: kept
+      end = nx.end;                                                            // collinear: dropped, move to the next point
+      tps += n_pos;
+    }
+  }
+  if (lane == 0) out[seg] = (double)((end + 1) - tps) / (double)N;
+}
+
 constexpr int SCAN_CHUNK_TILES = 2048;       // tiles per chunk of the two-level carry / finalize (long segments only)
 constexpr int SCAN_CHUNK_MIN_TILES = 8192;   // segments shorter than this stay single-level
 struct MetricsPlan {
@@ -759,7 +960,8 @@ int dml_ood_keystats(const float* values, int32_t score_kind, int32_t n_seg, int
 int dml_ood_keygen(const float* values, const float* minmax, int32_t minmax_slot, float* conf_out, const uint8_t* gt_u8,
                    const int64_t* gt_i64, uint64_t out_label_mask, const uint8_t* pos_u8, int32_t score_kind,
                    uint32_t key_base, int32_t n_seg, int64_t seg_len, uint32_t* keys, long long* seg_stats,
-                   const float* msp, float* msp_norm_out, float* mix_out, float lambda, float thr, dml_stream_t stream_) {
+                   const float* msp, float* msp_norm_out, float* mix_out, float lambda, float thr, void* sort_workspace,
+                   size_t sort_workspace_bytes, dml_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (!values || !keys || !seg_stats || n_seg < 0 || seg_len < 0 || n_seg > 65535) return DML_ERR_INVALID_ARG;
   const int nsrc = (gt_u8 != nullptr) + (gt_i64 != nullptr) + (pos_u8 != nullptr);
@@ -784,13 +986,30 @@ int dml_ood_keygen(const float* values, const float* minmax, int32_t minmax_slot
   dim3 grid((unsigned)bx, (unsigned)n_seg);
   unsigned long long* st = (unsigned long long*)seg_stats;
   const long long* g64 = (const long long*)gt_i64;
-  if (gt_i64) {
-    if (vec4) keygen_kernel<long long, 4><<<grid, 256, 0, stream>>>(values, minmax, minmax_slot, conf_out, g64, out_label_mask, nullptr, score_kind, seg_len, key_base, keys, st, fz);
-    else keygen_kernel<long long, 1><<<grid, 256, 0, stream>>>(values, minmax, minmax_slot, conf_out, g64, out_label_mask, nullptr, score_kind, seg_len, key_base, keys, st, fz);
-  } else {
-    if (vec4) keygen_kernel<uint8_t, 4><<<grid, 256, 0, stream>>>(values, minmax, minmax_slot, conf_out, gt_u8, out_label_mask, pos_u8, score_kind, seg_len, key_base, keys, st, fz);
-    else keygen_kernel<uint8_t, 1><<<grid, 256, 0, stream>>>(values, minmax, minmax_slot, conf_out, gt_u8, out_label_mask, pos_u8, score_kind, seg_len, key_base, keys, st, fz);
+  HistArgs hz = {};
+  const bool hist = sort_workspace != nullptr;
+  if (hist) {
+    // fused digit histograms for the full-key sort dml_ood_eval_segments(..., hist_precomputed = 1) will run
+    const SortPlan plan = make_sort_plan(n_seg, seg_len, 0, 32);
+    if (sort_workspace_bytes < plan.off_end) return DML_ERR_WORKSPACE;
+    hz.ghist = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(sort_workspace) + plan.off_hist);
+    hz.n_passes = plan.n_passes;
+    for (int p = 0; p < MAX_PASSES; ++p) hz.shifts[p] = plan.shifts[p];
+    DML_CUDA_TRY(cudaMemsetAsync(hz.ghist, 0, plan.off_lookback - plan.off_hist, stream));
   }
+#define DML_KEYGEN_LAUNCH(GT, V, gtp, posp)                                                                          \
+  do {                                                                                                                 \
+    if (hist) keygen_kernel<GT, V, true><<<grid, 256, 0, stream>>>(values, minmax, minmax_slot, conf_out, gtp, out_label_mask, posp, score_kind, seg_len, key_base, keys, st, fz, hz); \
+    else keygen_kernel<GT, V, false><<<grid, 256, 0, stream>>>(values, minmax, minmax_slot, conf_out, gtp, out_label_mask, posp, score_kind, seg_len, key_base, keys, st, fz, hz); \
+  } while (0)
+  if (gt_i64) {
+    if (vec4) DML_KEYGEN_LAUNCH(long long, 4, g64, nullptr);
+    else DML_KEYGEN_LAUNCH(long long, 1, g64, nullptr);
+  } else {
+    if (vec4) DML_KEYGEN_LAUNCH(uint8_t, 4, gt_u8, pos_u8);
+    else DML_KEYGEN_LAUNCH(uint8_t, 1, gt_u8, pos_u8);
+  }
+#undef DML_KEYGEN_LAUNCH
   DML_LAUNCH_CHECK();
   return DML_OK;
 }
@@ -801,7 +1020,8 @@ size_t dml_ood_workspace_bytes(int32_t n_seg, int64_t seg_len) {
 }
 
 int dml_ood_eval_segments(uint32_t* keys, const long long* seg_stats, int32_t n_seg, int64_t seg_len, double recall_level,
-                          void* workspace, size_t workspace_bytes, dml_ood_result* results, dml_stream_t stream_) {
+                          void* workspace, size_t workspace_bytes, int32_t hist_precomputed, dml_ood_result* results,
+                          dml_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (!keys || !seg_stats || !workspace || !results || n_seg < 0 || seg_len < 0 || n_seg > 65535) return DML_ERR_INVALID_ARG;
   if (seg_len >= (1ll << 32)) return DML_ERR_INVALID_ARG;
@@ -811,13 +1031,30 @@ int dml_ood_eval_segments(uint32_t* keys, const long long* seg_stats, int32_t n_
   unsigned char* ws = reinterpret_cast<unsigned char*>(workspace);
   uint32_t* sorted = keys;
   if (seg_len > 0) {
-    int rc = radix_sort_segments(keys, m.sort, workspace, &sorted, stream);
+    int rc = radix_sort_segments(keys, m.sort, workspace, &sorted, stream, hist_precomputed != 0);
     if (rc != DML_OK) return rc;
   }
   RangeInfo* info = reinterpret_cast<RangeInfo*>(ws + m.off_info);
   range_info_from_stats_kernel<<<ceil_div_i(n_seg, 256), 256, 0, stream>>>((const unsigned long long*)seg_stats, seg_len, n_seg, info);
   DML_LAUNCH_CHECK();
   return run_scan(sorted, m, ws, info, recall_level, (const unsigned long long*)seg_stats, results, nullptr, stream);
+}
+
+int dml_ood_roc_fpr(const uint32_t* keys, const long long* seg_stats, int32_t n_seg, int64_t seg_len, double recall_level,
+                    const void* workspace, size_t workspace_bytes, double* fpr_out, dml_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!keys || !seg_stats || !workspace || !fpr_out || n_seg < 0 || seg_len < 1 || n_seg > 65535) return DML_ERR_INVALID_ARG;
+  if (seg_len >= (1ll << 32)) return DML_ERR_INVALID_ARG;
+  if (n_seg == 0) return DML_OK;
+  const MetricsPlan m = make_metrics_plan(n_seg, seg_len);
+  if (workspace_bytes < m.off_end) return DML_ERR_WORKSPACE;
+  const unsigned char* ws = reinterpret_cast<const unsigned char*>(workspace);
+  // where dml_ood_eval_segments left the sorted keys: the ping-pong ends in `keys` after an even number of passes
+  const uint32_t* sorted = (m.sort.n_passes % 2 == 0) ? keys : reinterpret_cast<const uint32_t*>(ws + m.sort.off_alt);
+  roc_fpr_kernel<<<n_seg, SCAN_THREADS, 0, stream>>>(sorted, seg_len, m.tiles_per_seg, reinterpret_cast<const Carry*>(ws + m.off_carry),
+                                                     (const unsigned long long*)seg_stats, recall_level, fpr_out);
+  DML_LAUNCH_CHECK();
+  return DML_OK;
 }
 
 int dml_ood_sort(uint32_t* keys, int32_t n_seg, int64_t seg_len, int32_t begin_bit, int32_t end_bit, void* workspace,

@@ -332,7 +332,8 @@ SortPlan make_sort_plan(int n_seg, long long seg_len, int begin_bit, int end_bit
   return p;
 }
 
-int radix_sort_segments(uint32_t* keys, const SortPlan& plan, void* workspace, uint32_t** sorted, cudaStream_t stream) {
+int radix_sort_segments(uint32_t* keys, const SortPlan& plan, void* workspace, uint32_t** sorted, cudaStream_t stream,
+                        bool hist_done) {
   unsigned char* ws = reinterpret_cast<unsigned char*>(workspace);
   uint32_t* alt = reinterpret_cast<uint32_t*>(ws + plan.off_alt);
   uint32_t* ghist = reinterpret_cast<uint32_t*>(ws + plan.off_hist);
@@ -343,13 +344,15 @@ int radix_sort_segments(uint32_t* keys, const SortPlan& plan, void* workspace, u
     *sorted = keys;
     return DML_OK;
   }
-  DML_CUDA_TRY(cudaMemsetAsync(ghist, 0, plan.off_lookback - plan.off_hist, stream));
-  {
+  if (!hist_done) {
+    DML_CUDA_TRY(cudaMemsetAsync(ghist, 0, plan.off_lookback - plan.off_hist, stream));
     const long long chunk = (long long)HIST_TILES_PER_BLOCK * SORT_TILE;
     dim3 grid((unsigned)((plan.seg_len + chunk - 1) / chunk), (unsigned)plan.n_seg);
     hist_kernel<<<grid, SORT_THREADS, 0, stream>>>(keys, plan.seg_len, plan.n_passes, plan.shifts[0], plan.shifts[1],
                                                    plan.shifts[2], plan.shifts[3], ghist);
     DML_LAUNCH_CHECK();
+  }
+  {
     hist_scan_kernel<<<plan.n_seg * MAX_PASSES, RADIX, 0, stream>>>(ghist);
     DML_LAUNCH_CHECK();
   }

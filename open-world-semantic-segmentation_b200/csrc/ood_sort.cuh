@@ -37,6 +37,8 @@ struct SortPlan {
 
 SortPlan make_sort_plan(int n_seg, long long seg_len, int begin_bit, int end_bit);
 // sort; returns pointer to the buffer that holds the result (keys or the alt buffer in workspace)
-int radix_sort_segments(uint32_t* keys, const SortPlan& plan, void* workspace, uint32_t** sorted, cudaStream_t stream);
+// `hist_done`: the digit histograms in the workspace were already accumulated by the key-generation kernel
+int radix_sort_segments(uint32_t* keys, const SortPlan& plan, void* workspace, uint32_t** sorted, cudaStream_t stream,
+                        bool hist_done = false);
 
 }  // namespace dml

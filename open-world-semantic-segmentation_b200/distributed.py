@@ -57,7 +57,7 @@ class CudaOps:
             check(lib().dml_ood_keygen(ptr(conf.contiguous().view(-1)), None, 0, None,
                                        ptr(g) if g.dtype == torch.uint8 else None, ptr(g) if g.dtype == torch.int64 else None,
                                        ood.label_mask(out_labels), None, 0, key_base, 1, n, ptr(keys), ptr(stats),
-                                       None, None, None, 0.0, 0.0, stream_ptr(self.device)), "dml_ood_keygen")
+                                       None, None, None, 0.0, 0.0, None, 0, stream_ptr(self.device)), "dml_ood_keygen")
         return keys, stats
 
     def sort(self, keys, tag="a"):

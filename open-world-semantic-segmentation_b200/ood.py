@@ -8,6 +8,7 @@ generation, segmented radix sort, group scan, fixed-order reductions.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Iterable, Optional, Sequence
 
 import numpy as np
@@ -107,15 +108,37 @@ def eval_segments(values: torch.Tensor, n_seg: int, seg_len: int, *, gt: Optiona
             raise ValueError("gt must be uint8 or int64")
     else:
         raise ValueError("need gt or positive")
+    # batched segments: the sort's digit histograms are accumulated by the key-generation kernel (measured on B200:
+    # -1 ms per 1.38 G pairs for 50-image batches, +1.4 ms for one long segment, hence the n_seg rule;
+    # DML_FUSED_HIST=0 / 1 forces the separate / fused form)
+    fh = os.environ.get("DML_FUSED_HIST", "")
+    fused_hist = n > 0 and (fh == "1" or (fh != "0" and n_seg >= 4))
     with torch.cuda.device(dev):
         s = stream_ptr(dev)
         check(lib().dml_ood_keygen(ptr(values), ptr(minmax), minmax_slot, ptr(conf_out), ptr(gt_u8), ptr(gt_i64),
                                    label_mask(out_labels) if positive is None else 0, ptr(pos_u8), score_kind, key_base,
                                    n_seg, seg_len, ptr(keys), ptr(stats), ptr(msp), ptr(msp_norm_out), ptr(mix_out),
-                                   lam, thr, s), "dml_ood_keygen")
+                                   lam, thr, ptr(scratch) if fused_hist else None, scratch.numel() if fused_hist else 0, s),
+              "dml_ood_keygen")
         check(lib().dml_ood_eval_segments(ptr(keys), ptr(stats), n_seg, seg_len, recall_level, ptr(scratch),
-                                          scratch.numel(), ptr(results), s), "dml_ood_eval_segments")
+                                          scratch.numel(), 1 if fused_hist else 0, ptr(results), s), "dml_ood_eval_segments")
     return results, stats
+
+
+def roc_fpr_after_eval(workspace: "OodWorkspace", n_seg: int, seg_len: int,
+                       recall_level: float = RECALL_LEVEL_DEFAULT) -> torch.Tensor:
+    """Second FPR@recall convention for the segments just evaluated by ``eval_segments(..., workspace=workspace)``:
+    ``fpr[tpr >= recall_level][0]`` on ``sklearn.metrics.roc_curve`` with ``drop_intermediate=True``
+    (DeepLabV3Plus-Pytorch/test.py:241-244).  Returns a float64 device tensor [n_seg] (NaN: single class)."""
+    dev = workspace.device
+    keys = workspace.get("keys", 4 * n_seg * seg_len)
+    stats = workspace.get("stats", 32 * max(n_seg, 1)).view(torch.int64)[: 4 * n_seg].view(n_seg, 4)
+    scratch = workspace.get("scratch", lib().dml_ood_workspace_bytes(n_seg, seg_len))
+    out = torch.empty(n_seg, dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        check(lib().dml_ood_roc_fpr(ptr(keys), ptr(stats), n_seg, seg_len, recall_level, ptr(scratch), scratch.numel(),
+                                    ptr(out), stream_ptr(dev)), "dml_ood_roc_fpr")
+    return out
 
 
 def results_to_host(results: torch.Tensor, stats: torch.Tensor, what: str = "ood metrics"):
@@ -171,11 +194,15 @@ def combine_partials(partials: Sequence[np.ndarray], total_pos: int, total_n: in
 
 
 def measures_from_scores(scores: torch.Tensor, positive: torch.Tensor, recall_level: float = RECALL_LEVEL_DEFAULT,
-                         workspace: Optional[OodWorkspace] = None):
+                         workspace: Optional[OodWorkspace] = None, fpr_convention: str = "closest"):
     """(auroc, aupr, fpr) for arbitrary fp32 scores (higher = more positive) and a 0/1 mask.
+    ``fpr_convention``: "closest" = anomaly/anom_utils.py:57-65 (recall closest to the level);
+    "roc_curve" = ``fpr[tpr >= level][0]`` on sklearn's ``roc_curve`` (DeepLabV3Plus-Pytorch/test.py:242-244).
     One segment; the packed-key window is chosen from the data (one extra read of the scores);
     mixed-sign inputs whose keys span more than 31 bits are ranked as two ranges (score > 0,
     then score <= 0) that are sorted separately and scanned with carried counts."""
+    if fpr_convention not in ("closest", "roc_curve"):
+        raise ValueError("fpr_convention must be 'closest' or 'roc_curve'")
     require_cuda(scores, "scores")
     dev = scores.device
     scores = scores.contiguous().view(-1).float()
@@ -193,8 +220,13 @@ def measures_from_scores(scores: torch.Tensor, positive: torch.Tensor, recall_le
         if kmax - kmin < (1 << 31):
             res, stats = eval_segments(scores, 1, n, positive=positive, score_kind=1, key_base=kmin,
                                        recall_level=recall_level, workspace=ws)
+            roc = roc_fpr_after_eval(ws, 1, n, recall_level) if fpr_convention == "roc_curve" else None
             vals, counts = results_to_host(res, stats)
-            return float(vals[0, 0]), float(vals[0, 1]), float(vals[0, 2])
+            fpr = float(vals[0, 2]) if roc is None else float(roc.cpu()[0])
+            return float(vals[0, 0]), float(vals[0, 1]), fpr
+        if fpr_convention == "roc_curve":
+            raise NotImplementedError("roc_curve FPR convention: scores must span less than 2^31 sortable key values "
+                                      "(always true for same-sign scores such as 1 - max softmax)")
         # wide, mixed-sign range: keys of positive scores (negative ranking key) come first
         first = scores > 0
         parts = [(scores[first], positive[first]), (scores[~first], positive[~first])]
@@ -210,7 +242,7 @@ def measures_from_scores(scores: torch.Tensor, positive: torch.Tensor, recall_le
             keys = ws.get("keys", 4 * m)
             stats = ws.get("stats", 32).view(torch.int64)[:4].view(1, 4)
             check(lib().dml_ood_keygen(ptr(sc), None, 0, None, None, None, 0, ptr(po), 1, base, 1, m, ptr(keys),
-                                       ptr(stats), None, None, None, 0.0, 0.0, stream_ptr(dev)), "dml_ood_keygen")
+                                       ptr(stats), None, None, None, 0.0, 0.0, None, 0, stream_ptr(dev)), "dml_ood_keygen")
             nbytes = lib().dml_ood_workspace_bytes(1, m)
             scratch = ws.get("scratch", nbytes)
             sorted_ptr = C.c_void_p()

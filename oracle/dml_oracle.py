@@ -387,6 +387,35 @@ def average_precision(y_true: np.ndarray, y_score: np.ndarray) -> float:
     return float(max(0.0, -np.sum(np.diff(recall) * precision[:-1])))
 
 
+def roc_curve_drop_intermediate(y_true: np.ndarray, y_score: np.ndarray):
+    """``sklearn.metrics.roc_curve(y_true, y_score)`` with its default ``drop_intermediate=True`` as the
+    softmax-baseline evaluator calls it (DeepLabV3Plus-Pytorch/test.py:242): points of the distinct-threshold
+    curve whose second differences of fps AND tps vanish (collinear with both neighbours) are dropped, the
+    first and last are always kept, then (0, 0) is prepended.  scikit-learn is not vendored in the reference
+    (pinned 0.24.1, requirements.txt:111; same rule in the installed 1.9.0, _ranking.py roc_curve).
+    Returns (fpr, tpr) float64."""
+    fps, tps, _ = binary_clf_curve(y_true, y_score)
+    if len(fps) > 2:
+        keep = np.where(np.r_[True, np.logical_or(np.diff(fps, 2), np.diff(tps, 2)), True])[0]
+        fps, tps = fps[keep], tps[keep]
+    tps = np.r_[0, tps]
+    fps = np.r_[0, fps]
+    fpr = fps / fps[-1] if fps[-1] > 0 else np.repeat(np.nan, fps.shape)
+    tpr = tps / tps[-1] if tps[-1] > 0 else np.repeat(np.nan, tps.shape)
+    return fpr, tpr
+
+
+def baseline_roc_measures(msk_auc: np.ndarray, scores_auc: np.ndarray, recall_level: float = 0.95):
+    """(auc, aupr, fpr95) of the softmax-baseline evaluator, DeepLabV3Plus-Pytorch/test.py:241-244:
+    ``roc_auc_score``, ``average_precision_score`` and ``fpr95 = fpr[tpr >= 0.95][0]`` on ``roc_curve``
+    -- the FIRST kept ROC point whose recall reaches the level (not the closest-recall rule of
+    anomaly/anom_utils.py:57-65)."""
+    y = np.asarray(msk_auc).astype(np.int64).ravel()
+    s = np.asarray(scores_auc).ravel()
+    fpr, tpr = roc_curve_drop_intermediate(y, s)
+    return roc_auc(y, s), average_precision(y, s), float(fpr[tpr >= recall_level][0])
+
+
 def _check_finite(a: np.ndarray):
     if not np.all(np.isfinite(a)):
         raise ValueError("Input contains NaN or infinity.")  # sklearn's check_array behaviour

@@ -492,6 +492,50 @@ def gen_segmetrics():
     save("segmetrics.npz", **out)
 
 
+def gen_roc_baseline():
+    """Softmax-baseline evaluator of DeepLabV3Plus-Pytorch/test.py:241-244, which calls scikit-learn directly
+    (``import sklearn.metrics as Metrics``): roc_auc_score, roc_curve (drop_intermediate default),
+    average_precision_score, fpr95 = fpr[tpr >= 0.95][0].  Cases stress the drop_intermediate rule: runs of
+    consecutive groups with identical (pos, neg) counts around the 95 % recall point, ties, plateaus."""
+    import sklearn.metrics as Metrics
+    rng = np.random.default_rng(77)
+    cases = {}
+    # continuous scores (every group has one element)
+    s = rng.random(20000).astype(np.float32)
+    y = (rng.random(20000) < 0.05 + 0.3 * s).astype(np.int64)
+    cases["continuous"] = (y, s)
+    # coarse quantisation: large groups, many with equal counts
+    s = (rng.integers(0, 40, 30000) / 40).astype(np.float32)
+    y = (rng.random(30000) < 0.2).astype(np.int64)
+    cases["quantised"] = (y, s)
+    # pairs (1 pos, 1 neg) per score value over a long stretch covering the recall point: collinear diagonal
+    k = 2000
+    s = np.repeat(np.arange(k, dtype=np.float32) / k, 2)
+    y = np.tile(np.array([1, 0]), k)
+    cases["diagonal_pairs"] = (y, s)
+    # same, but the stretch ends right after the recall point
+    s2 = s.copy(); y2 = y.copy()
+    y2[:150] = 0
+    cases["diagonal_then_negatives"] = (y2, s2)
+    # plateau at the top score holding > 95 % of the positives (first point already reaches the level)
+    s = rng.random(5000).astype(np.float32) * 0.5
+    y = np.zeros(5000, np.int64)
+    s[:300] = 0.9; y[:290] = 1; y[4000:4010] = 1
+    cases["plateau_first_point"] = (y, s)
+    # tiny
+    cases["tiny"] = (np.array([1, 0, 1, 1, 0, 0, 1, 0]), np.float32([.9, .8, .8, .7, .7, .3, .2, .1]))
+    out = {}
+    for name, (y, s) in cases.items():
+        auc = Metrics.roc_auc_score(y, s)
+        fpr, tpr, _ = Metrics.roc_curve(y, s)
+        aupr = Metrics.average_precision_score(y, s)
+        out[f"{name}_y"] = y.astype(np.uint8)
+        out[f"{name}_s"] = s.astype(np.float32)
+        out[f"{name}_res"] = np.float64([auc, aupr, fpr[tpr >= 0.95][0]])
+        out[f"{name}_fpr90"] = np.float64(fpr[tpr >= 0.90][0])
+    save("roc_baseline.npz", **out)
+
+
 def main():
     import sklearn
     import scipy
@@ -503,6 +547,7 @@ def main():
     gen_plm()
     gen_loss()
     gen_segmetrics()
+    gen_roc_baseline()
     meta = {"python": sys.version.split()[0], "torch": torch.__version__, "numpy": np.__version__,
             "sklearn": sklearn.__version__, "scipy": scipy.__version__,
             "reference": "/root/reference (Jun-CEN/Open-World-Semantic-Segmentation, unmodified)"}

@@ -213,3 +213,16 @@ def test_masked_class_mean_matches_per_class_sums():
     sums, cnt = O.per_class_sums(f.reshape(-1, 16), lab.reshape(-1), 19)
     np.testing.assert_allclose(m, sums[15] / cnt[15], rtol=1e-5)
     assert O.masked_class_mean(f, np.zeros_like(lab), 15) is None
+
+
+ROC_CASES = ["continuous", "quantised", "diagonal_pairs", "diagonal_then_negatives", "plateau_first_point", "tiny"]
+
+
+@pytest.mark.parametrize("name", ROC_CASES)
+def test_baseline_roc_measures_golden(golden, name):
+    """softmax-baseline evaluator (DeepLabV3Plus-Pytorch/test.py:241-244): the oracle's restatement of
+    roc_auc_score / average_precision_score / roc_curve(drop_intermediate) vs scikit-learn's own outputs"""
+    g = golden("roc_baseline.npz")
+    y, s = g[f"{name}_y"].astype(np.int64), g[f"{name}_s"]
+    np.testing.assert_allclose(O.baseline_roc_measures(y, s), g[f"{name}_res"], rtol=0, atol=1e-15)
+    assert O.baseline_roc_measures(y, s, 0.90)[2] == float(g[f"{name}_fpr90"])
