@@ -317,7 +317,8 @@ class Pipeline:
             self.pooled_result = (res, stats)
         else:
             from dml_b200 import distributed as D
-            self.pooled_result = D.pooled_measures(self.conf.view(-1), gt_all.view(-1), (self.k,), workspace=self.ws_pool)
+            self.pooled_result = D.pooled_measures(self.conf.view(-1), gt_all.view(-1), (self.k,), workspace=self.ws_pool,
+                                                   timing=True)
 
     def step_resident(self, x_all, gt_all, time_head=False):
         self.confusion.zero_()
@@ -332,6 +333,26 @@ class Pipeline:
             self.pooled_events.append((p0, p1))
 
 
+def bind_to_gpu_numa_node(index):
+    """Pin this process to the CPUs NVML reports as local to GPU `index`, BEFORE any pinned host buffer is allocated,
+    so that first-touch places the staging ring on the GPU's own NUMA node (8 ranks feeding 8 GPUs otherwise pull
+    half of their H2D traffic across the socket interconnect).  Best effort: any failure leaves the affinity alone."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        cpus = {w * 64 + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -340,6 +361,7 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    numa_cpus = bind_to_gpu_numa_node(local) if world > 1 else None
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback; use --impl reference)"
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
@@ -347,6 +369,10 @@ def run_ours(args):
         # keep stdout to the ONE JSON line: NCCL prints its version banner to stdout at NCCL_DEBUG=VERSION
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"
+        # the one large collective of the step is the all-to-all of the key ranges (send/recv pairs): give the p2p
+        # path every channel (measured with tools/bench_a2a.py on 2 x B200: 431 -> 632 GB/s per direction)
+        for k, v in (("NCCL_MIN_P2P_NCHANNELS", "64"), ("NCCL_MAX_P2P_NCHANNELS", "64"), ("NCCL_MIN_NCHANNELS", "64")):
+            os.environ.setdefault(k, v)
         dist.init_process_group("nccl", device_id=device)
     lib = dml_b200.load_library()
     k, h, w, n = args.classes, args.height, args.width, args.images
@@ -445,6 +471,10 @@ def run_ours(args):
                        "bytes_per_pair_model": 53 if world == 1 else None,
                        "achieved_GBps": (tot_px * 53 / (sum(pool_ms) * 1e-3) / 1e9) if world == 1 else None,
                        "Gpairs_per_s": tot_px / (sum(pool_ms) * 1e-3) / 1e9})
+        if world > 1 and pipe.pooled_result is not None:
+            info = pipe.pooled_result[3]
+            stages[-1]["phases_ms_last_step_rank0"] = {k: round(v, 3) for k, v in info.get("phase_ms", {}).items()}
+            stages[-1]["exchanged_bytes_rank0"] = info.get("exchanged_bytes")
     roofline["stages"] = stages
 
     # ---- results (also the parity self-check of the bench) ------------------------------------------
@@ -494,7 +524,8 @@ def run_ours(args):
                            "range partition of the unsorted keys + NCCL all-to-all + one local sort per rank (mode=partition)"},
                 "roofline": roofline, "cpu_baseline": cpu,
                 "e2e": ({"value": e2e["value"], "unit": UNIT, "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
-                         "ms_per_step": e2e["ms_per_step"], "steps": e2e["steps"], "note": e2e["note"]} if e2e else None),
+                         "ms_per_step": e2e["ms_per_step"], "steps": e2e["steps"], "note": e2e["note"],
+                         "cpus_bound_to_gpu_numa_node": numa_cpus} if e2e else None),
                 "gpu_launches": int(launches), "clocks": clocks, "results": summary}
         print(json.dumps(line))
     if world > 1:

@@ -163,7 +163,8 @@ def choose_splitters(all_samples: torch.Tensor, world: int) -> torch.Tensor:
 
 def pooled_measures(conf: torch.Tensor, gt: torch.Tensor, out_labels: Sequence[int] = (13,), *, group=None,
                     recall_level: float = ood.RECALL_LEVEL_DEFAULT, mode: str = "partition", ops=None,
-                    workspace: Optional[ood.OodWorkspace] = None, key_base: int = ood.KEY_BASE_NONNEG):
+                    workspace: Optional[ood.OodWorkspace] = None, key_base: int = ood.KEY_BASE_NONNEG,
+                    timing: bool = False):
     """Exact pooled (auroc, aupr, fpr, info) over the (conf, gt) pairs of ALL ranks of ``group``.
     ``conf`` must be non-negative (normalised maps); positives are gt in ``out_labels``; the ranked
     score is -conf like anomaly/eval_ood_traditional.py:139-141.  Collective: every rank must call it."""
@@ -173,8 +174,18 @@ def pooled_measures(conf: torch.Tensor, gt: torch.Tensor, out_labels: Sequence[i
     rank = dist.get_rank(group)
     ops = ops or CudaOps(conf.device, workspace)
     dev = conf.device
+    marks = []
 
+    def mark(name):
+        # CUDA-event phase boundaries on the current stream (``timing=True``; CUDA tensors only)
+        if timing and conf.is_cuda:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record(torch.cuda.current_stream(dev))
+            marks.append((name, ev))
+
+    mark("start")
     keys, stats = ops.make_keys(conf, gt, out_labels, key_base)
+    mark("keygen")
     partition = mode == "partition"
     n_local = keys.numel()
     # ---- splitters from a sample of every shard (regular sample of the sorted shard, or a strided sample of
@@ -193,8 +204,10 @@ def pooled_measures(conf: torch.Tensor, gt: torch.Tensor, out_labels: Sequence[i
     bounds = choose_splitters(vals, world)                       # int64 [world+1]
     q = (bounds[:-1] & 0xFFFFFFFF).to(torch.int64)
     queries = torch.where(q >= (1 << 31), q - (1 << 32), q).to(torch.int32)   # bit patterns
+    mark("local_sort+sample+splitters")
     if partition:
         srt, cnt_dev = ops.partition(keys, queries[1:])           # grouped by range, not sorted
+        mark("partition")
         send_counts = cnt_dev.cpu().tolist()
     else:
         cuts = ops.lower_bound(srt, queries)                      # [world] start of every range in my shard
@@ -219,6 +232,7 @@ def pooled_measures(conf: torch.Tensor, gt: torch.Tensor, out_labels: Sequence[i
     m = int(sum(recv_counts))
     mine = ops.empty_keys(m, "range")
     moved_bytes = 0
+    mark("counts_exchange")
     if mode in ("alltoall", "partition"):
         dist.all_to_all_single(mine, srt, recv_counts, send_counts, group=group)
         moved_bytes = 4 * (m - recv_counts[rank])
@@ -237,8 +251,10 @@ def pooled_measures(conf: torch.Tensor, gt: torch.Tensor, out_labels: Sequence[i
             off += c
         moved_bytes = 4 * int(sum(sizes) - sizes[rank])
 
+    mark("key_exchange")
     # ---- merge (re-sort) my range, carry the counts that precede it, scan -----------------------------------
     merged = ops.sort(mine, "merge")
+    mark("range_sort")
     pos_r = ops.count_positive(merged)
     pr = torch.cat([pos_r.view(1), torch.tensor([m], dtype=torch.int64, device=dev)])
     all_pr = [torch.empty_like(pr) for _ in range(world)]
@@ -247,12 +263,19 @@ def pooled_measures(conf: torch.Tensor, gt: torch.Tensor, out_labels: Sequence[i
     pos_before = int(all_pr[:rank, 0].sum())
     idx_before = int(all_pr[:rank, 1].sum())
     info = torch.tensor([pos_before, idx_before, total_pos, total_n], dtype=torch.int64, device=dev)
+    mark("carry_exchange")
     partial = ops.scan_range(merged, info, recall_level)
+    mark("range_scan")
     parts = [torch.empty_like(partial) for _ in range(world)]
     dist.all_gather(parts, partial, group=group)
     auroc, aupr, fpr, groups = ood.combine_partials([p.cpu().numpy() for p in parts], total_pos, total_n, recall_level)
-    return auroc, aupr, fpr, {"n_pos": total_pos, "n_neg": total_n - total_pos, "n_groups": groups, "range_keys": m,
-                               "exchanged_bytes": moved_bytes, "mode": mode}
+    mark("combine")
+    out = {"n_pos": total_pos, "n_neg": total_n - total_pos, "n_groups": groups, "range_keys": m,
+           "exchanged_bytes": moved_bytes, "mode": mode}
+    if marks:
+        marks[-1][1].synchronize()
+        out["phase_ms"] = {b[0]: a[1].elapsed_time(b[1]) for a, b in zip(marks[:-1], marks[1:])}
+    return auroc, aupr, fpr, out
 
 
 def mean_of_per_image(per_image_vals: torch.Tensor, group=None):
