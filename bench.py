@@ -50,6 +50,9 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-pooled", action="store_true")
+    ap.add_argument("--pooled-keys", default=os.environ.get("DML_BENCH_POOLED_KEYS", "reuse"), choices=["reuse", "regenerate"],
+                    help="pooled metric: reuse the ranking keys / digit histograms of the per-image pass (ood.KeyPool), or "
+                         "regenerate them from the conf maps in a second pass")
     return ap.parse_args()
 
 
@@ -273,6 +276,10 @@ class Pipeline:
         self.per_image_stats = torch.empty(n, 4, dtype=torch.int64, device=device)
         self.ws_img = ood.OodWorkspace(device)
         self.ws_pool = ood.OodWorkspace(device)
+        # the per-image pass leaves its packed keys (and, on one GPU, their digit histograms) for the pooled metric
+        self.pool = None
+        if not args.no_pooled and args.pooled_keys == "reuse":
+            self.pool = ood.KeyPool(n * self.hw, device, workspace=self.ws_pool, histograms=(world == 1))
         self.outs = []
         for (s, e) in self.bounds:
             self.outs.append(H.HeadOutput(label=self.label[s:e], eds=self.eds[s:e], msp=self.msp[s:e],
@@ -281,6 +288,11 @@ class Pipeline:
         self.metric_events = []
         self.pooled_events = []
         self.pooled_result = None
+
+    def begin_step(self):
+        self.confusion.zero_()
+        if self.pool is not None:
+            self.pool.reset()
 
     # one chunk: head -> finalize (MMSP + mix maps) -> fused-normalisation key-gen + per-image metrics
     def process_chunk(self, ci, x, gt, time_head=False):
@@ -301,7 +313,7 @@ class Pipeline:
         res, stats = ood.eval_segments(self.eds[s:e], nb, self.hw, gt=gt, out_labels=(self.k,), score_kind=0,
                                        minmax=self.minmax[s:e], minmax_slot=0, conf_out=self.conf[s:e],
                                        workspace=self.ws_img, msp=self.msp[s:e], msp_norm_out=self.mmsp_c[:nb],
-                                       mix_out=self.mix_c[:nb])
+                                       mix_out=self.mix_c[:nb], pool=self.pool)
         if time_head:
             ev2.record()
             self.metric_events.append((ev1, ev2))
@@ -312,16 +324,19 @@ class Pipeline:
         if self.args.no_pooled:
             return
         if self.world == 1:
-            res, stats = self.ood.eval_segments(self.conf.view(-1), 1, self.n * self.hw, gt=gt_all.view(-1),
-                                                out_labels=(self.k,), score_kind=0, workspace=self.ws_pool)
-            self.pooled_result = (res, stats)
+            if self.pool is not None:
+                self.pooled_result = self.pool.evaluate()
+            else:
+                self.pooled_result = self.ood.eval_segments(self.conf.view(-1), 1, self.n * self.hw, gt=gt_all.view(-1),
+                                                            out_labels=(self.k,), score_kind=0, workspace=self.ws_pool)
         else:
             from dml_b200 import distributed as D
+            ks = (self.pool.keys, self.pool.stats[0]) if self.pool is not None else None
             self.pooled_result = D.pooled_measures(self.conf.view(-1), gt_all.view(-1), (self.k,), workspace=self.ws_pool,
-                                                   timing=True)
+                                                   timing=True, keys_and_stats=ks)
 
     def step_resident(self, x_all, gt_all, time_head=False):
-        self.confusion.zero_()
+        self.begin_step()
         for ci, (s, e) in enumerate(self.bounds):
             self.process_chunk(ci, x_all[s:e], gt_all[s:e], time_head)
         if time_head:
@@ -454,7 +469,8 @@ def run_ours(args):
     # the other stages of the step, from the same CUDA-event timeline (traffic MODELS, stated per pair):
     #   per-image metrics: key-gen (read eds 4 + msp 4 + gt 1, write conf 4 + mmsp 4 + mix 4 + key 4) + digit histograms
     #   (read 4) + 4 radix passes (read 4 + write 4) + tie-aware scan (2 reads of 4) = 69 B / pair
-    #   pooled metrics (1 GPU): key-gen (read conf 4 + gt 1, write key 4) + hist 4 + 4 x 8 + scan 8 = 53 B / pair
+    #   pooled metrics (1 GPU): key-gen (read conf 4 + gt 1, write key 4) + hist 4 + 4 x 8 + scan 8 = 53 B / pair;
+    #   with the per-image pass's keys and histograms reused (--pooled-keys reuse): 4 x 8 + scan 8 = 40 B / pair
     met_ms = [a.elapsed_time(b) for a, b in pipe.metric_events]
     pool_ms = [a.elapsed_time(b) for a, b in pipe.pooled_events]
     stages = [{"stage": "head (dominant streaming kernel, roofline above)", "ms_per_step": sum(head_ms) / args.steps,
@@ -465,11 +481,12 @@ def run_ours(args):
                        "ms_per_step": sum(met_ms) / args.steps, "share_of_step": sum(met_ms) / ms_total,
                        "bytes_per_pair_model": 69, "achieved_GBps": gbs, "frac_of_hbm_peak": gbs / peak,
                        "Gpairs_per_s": tot_px / (sum(met_ms) * 1e-3) / 1e9})
+    pool_bpp = 40 if pipe.pool is not None else 53
     if pool_ms and not args.no_pooled:
         stages.append({"stage": "pooled exact metrics over all pairs of the step" + (" (local part + NCCL exchange)" if world > 1 else ""),
                        "ms_per_step": sum(pool_ms) / args.steps, "share_of_step": sum(pool_ms) / ms_total,
-                       "bytes_per_pair_model": 53 if world == 1 else None,
-                       "achieved_GBps": (tot_px * 53 / (sum(pool_ms) * 1e-3) / 1e9) if world == 1 else None,
+                       "bytes_per_pair_model": pool_bpp if world == 1 else None,
+                       "achieved_GBps": (tot_px * pool_bpp / (sum(pool_ms) * 1e-3) / 1e9) if world == 1 else None,
                        "Gpairs_per_s": tot_px / (sum(pool_ms) * 1e-3) / 1e9})
         if world > 1 and pipe.pooled_result is not None:
             info = pipe.pooled_result[3]
@@ -520,8 +537,10 @@ def run_ours(args):
                 "data": "synthetic",
                 "config": {"workload": workload_name(args), "images_per_gpu": n, "chunk_images": pipe.chunk,
                            "l2": "inputs (%.1f GB/step/GPU) far exceed the 126 MB L2; no flush needed" % (n * k * hw * 4 / 1e9),
-                           "pooled": "single GPU sort" if world == 1 else
-                           "range partition of the unsorted keys + NCCL all-to-all + one local sort per rank (mode=partition)"},
+                           "pooled": ("single GPU sort" if world == 1 else
+                                      "range partition of the unsorted keys + NCCL all-to-all + one local sort per rank (mode=partition)") +
+                                     ("; keys" + (" and digit histograms" if world == 1 else "") + " reused from the per-image pass"
+                                      if pipe.pool is not None else "; keys regenerated from the conf maps")},
                 "roofline": roofline, "cpu_baseline": cpu,
                 "e2e": ({"value": e2e["value"], "unit": UNIT, "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
                          "ms_per_step": e2e["ms_per_step"], "steps": e2e["steps"], "note": e2e["note"],
@@ -563,7 +582,7 @@ def run_e2e(args, pipe, x_all, gt_all, device, world, barrier):
     def one_step():
         nonlocal h2d, d2h
         h2d = d2h = 0
-        pipe.confusion.zero_()
+        pipe.begin_step()
         ready = [torch.cuda.Event() for _ in pipe.bounds]
         done = [torch.cuda.Event() for _ in pipe.bounds]
         for ci, (s, e) in enumerate(pipe.bounds):

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define DML_B200_ABI_VERSION 2
+#define DML_B200_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define DML_API __attribute__((visibility("default")))
@@ -269,6 +269,20 @@ DML_API size_t dml_ood_workspace_bytes(int32_t n_seg, int64_t seg_len);
 DML_API int dml_ood_eval_segments(uint32_t* keys, const long long* seg_stats, int32_t n_seg, int64_t seg_len,
                           double recall_level, void* workspace, size_t workspace_bytes, int32_t hist_precomputed,
                           dml_ood_result* results, dml_stream_t stream);
+
+/* Pooled metric over the pairs of MANY dml_ood_keygen / dml_ood_eval_segments calls without generating or counting
+ * the keys a second time (the reference pools nothing; BASELINE.json's north star asks for the exact full-set
+ * AUROC / FPR95 next to the per-image mean of anomaly/eval_ood_traditional.py:569,641).  Call between
+ * dml_ood_keygen(..., sort_workspace = seg_workspace) and dml_ood_eval_segments(..., hist_precomputed = 1) of a
+ * batch: the batch's per-segment digit histograms (still raw counts at that point) are added to the histogram slot
+ * of `pooled_workspace`, the workspace of ONE segment of `pooled_len` keys (dml_ood_workspace_bytes(1, pooled_len));
+ * `reset` != 0 overwrites instead of adding (first batch of a pooled evaluation).  When every batch wrote its keys
+ * into consecutive slices of one buffer (all with the same key_base / score_kind), that buffer -- in whatever order
+ * the per-batch sorts left it -- is then evaluated with
+ *   dml_ood_eval_segments(all_keys, summed_seg_stats, 1, pooled_len, level, pooled_workspace, bytes, 1, result). */
+DML_API int dml_ood_pool_histograms(const void* seg_workspace, size_t seg_workspace_bytes, int32_t n_seg, int64_t seg_len,
+                            void* pooled_workspace, size_t pooled_workspace_bytes, int64_t pooled_len, int32_t reset,
+                            dml_stream_t stream);
 
 /* Second FPR@recall convention, used by the reference's softmax-baseline evaluator
  * (DeepLabV3Plus-Pytorch/test.py:241-244): fpr[tpr >= recall_level][0] on

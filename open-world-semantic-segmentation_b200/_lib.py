@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libdml_b200.so")
 
 DML_OK = 0
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 c_f32p = C.c_void_p
 c_void_p = C.c_void_p
@@ -98,6 +98,8 @@ SIGNATURES = {
     "dml_ood_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int64]),
     "dml_ood_eval_segments": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_double, C.c_void_p,
                                         C.c_size_t, C.c_int32, C.c_void_p, C.c_void_p]),
+    "dml_ood_pool_histograms": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int32, C.c_int64, C.c_void_p, C.c_size_t, C.c_int64,
+                                          C.c_int32, C.c_void_p]),
     "dml_ood_roc_fpr": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_double, C.c_void_p, C.c_size_t,
                                   C.c_void_p, C.c_void_p]),
     "dml_ood_sort": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_size_t,

@@ -400,6 +400,84 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_kernel(const HeadArgs a) {
     }
   }
 
+  int label[VEC];
+  float smin[VEC], eds[VEC], mspv[VEC];
+  if constexpr (IDENT && !EXTRA) {
+    // ---- lean scoring path for mu = m I (no per-class distance is ever formed) --------------------------------
+    // With S = sum_k x_k^2 and t_k = (x_k - m)^2 the K = D distances are d_k = S - x_k^2 + t_k, hence
+    //   sum_k d_k        = (D-1) S + sum_k t_k                       (EDS over all classes)
+    //   sum_{k>=1} d_k   = (D-2) S + x_0^2 + sum_{k>=1} t_k          (EDS with class 0 excluded)
+    // -- sums of non-negative terms only, so nothing cancels even when a pixel sits on its prototype -- and
+    // d_k - d_j = -2 m (x_k - x_j) exactly: the nearest prototype is the largest (m >= 0) / smallest (m < 0)
+    // channel, first index on ties like torch.max.  The max-softmax needs the same extremum (see below), so the
+    // label costs one compare + select per class and the distances of the losing classes cost nothing.
+    const bool sk = skip0 && D > 1;
+    const bool up = a.msp_scale >= 0.f;
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      float s0 = x[0][v] * x[0][v], s1 = 0.f, t0 = 0.f, t1 = 0.f;   // two interleaved chains each (ILP, shorter error chains)
+#pragma unroll
+      for (int k = 1; k < D; ++k) {
+        const float t = x[k][v] - a.diag_m;
+        if (k & 1) { s1 = fmaf(x[k][v], x[k][v], s1); t1 = fmaf(t, t, t1); }
+        else       { s0 = fmaf(x[k][v], x[k][v], s0); t0 = fmaf(t, t, t0); }
+      }
+      const float S = s0 + s1, T1 = t0 + t1;
+      const float u0 = x[0][v] - a.diag_m;
+      float e = sk ? fmaf((float)(D - 2), S, fmaf(x[0][v], x[0][v], T1)) : fmaf((float)(D - 1), S, fmaf(u0, u0, T1));
+      if (a.clamp > 0.f) e = (e >= a.clamp) ? a.clamp : e;
+      eds[v] = e;
+      // extremum over the score classes (ext_s) and over all classes (ext_all)
+      float ext1 = x[D > 1 ? 1 : 0][v];
+#pragma unroll
+      for (int k = 2; k < D; ++k) ext1 = up ? fmaxf(ext1, x[k][v]) : fminf(ext1, x[k][v]);
+      const float ext_all = D > 1 ? (up ? fmaxf(ext1, x[0][v]) : fminf(ext1, x[0][v])) : x[0][v];
+      const float ext_s = sk ? ext1 : ext_all;
+      int lab = 0;
+#pragma unroll
+      for (int k = D - 1; k >= 1; --k) lab = (x[k][v] == ext_all) ? k : lab;
+      label[v] = (x[0][v] == ext_all) ? 0 : lab;
+      // softmax_k(z) == softmax_k(2 m x_k): max-softmax = 1 / sum_k exp2(c x_k - c x_ext), c = 2 m log2(e).
+      // The sum lies in [1, D]: MUFU.RCP + one Newton step (<= 1 ulp) replaces the IEEE division sequence.
+      float pr = 0.f;
+      if (want_msp) {
+        const float c = a.msp_scale;
+        const float off = -c * ext_s;
+        float s = sk ? 0.f : ex2_approx(fmaf(c, x[0][v], off));
+#pragma unroll
+        for (int k = 1; k < D; ++k) s += ex2_approx(fmaf(c, x[k][v], off));
+        const float r = rcp_approx(s);
+        pr = fmaf(r, fmaf(-s, r, 1.0f), r);
+      }
+      mspv[v] = pr;
+      smin[v] = 0.f;
+    }
+    if (om & OUT_MAXLOGIT) {
+      // max logit = -(distance to the nearest score class ls): leave-one-out sum of squares + (x_ls - m)^2,
+      // where x_ls is the extremum itself
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) {
+        float ext1 = x[D > 1 ? 1 : 0][v];
+#pragma unroll
+        for (int k = 2; k < D; ++k) ext1 = up ? fmaxf(ext1, x[k][v]) : fminf(ext1, x[k][v]);
+        int ls = label[v];
+        float xe = x[0][v];
+        if (sk) {
+          ls = 1;
+#pragma unroll
+          for (int k = D - 1; k >= 1; --k) ls = (x[k][v] == ext1) ? k : ls;
+          xe = ext1;
+        } else if (D > 1) {
+          xe = up ? fmaxf(ext1, x[0][v]) : fminf(ext1, x[0][v]);
+        }
+        float r = 0.f;
+#pragma unroll
+        for (int d = 0; d < D; ++d) r = (d == ls) ? r : fmaf(x[d][v], x[d][v], r);
+        const float t = xe - a.diag_m;
+        smin[v] = fmaf(t, t, r);
+      }
+    }
+  } else {
   // per pixel: d0 = distance to class 0; (dmin1, arg1) = best of classes >= 1; esum1 = sum over classes >= 1
   float d0[VEC], dmin1[VEC], esum1[VEC], ssum[VEC];
   int arg1[VEC];
@@ -550,8 +628,7 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_kernel(const HeadArgs a) {
   // ---- per-pixel results ---------------------------------------------------------------
   // label = argmin over ALL classes (first minimum wins, like torch.max on the logits);
   // scores (eds, maxlogit, msp) over the score classes (all, or all but class 0)
-  int label[VEC];
-  float dbest[VEC], smin[VEC], eds[VEC], mspv[VEC];
+  float dbest[VEC];
 #pragma unroll
   for (int v = 0; v < VEC; ++v) {
     const bool zero_wins = (K == 1) || !(dmin1[v] < d0[v]);
@@ -578,6 +655,8 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_kernel(const HeadArgs a) {
       }
     }
   }
+
+  }  // generic (per-class distance) path
 
   const long long pix = (long long)b * a.HW + p0;
   if (active) {

@@ -932,6 +932,14 @@ int run_scan(const uint32_t* sorted, const MetricsPlan& m, unsigned char* ws, co
   return DML_OK;
 }
 
+// pooled[p][d] (+)= sum over segments of seg_hist[seg][p][d]; one thread per (pass, digit), coalesced over digits
+__global__ void __launch_bounds__(RADIX) pool_hist_kernel(const uint32_t* __restrict__ seg_hist, int n_seg,
+                                                          uint32_t* __restrict__ pooled, int reset) {
+  const int i = blockIdx.x * RADIX + threadIdx.x;   // p * RADIX + d
+  uint32_t c = reset ? 0u : pooled[i];
+  for (int s = 0; s < n_seg; ++s) c += seg_hist[(size_t)s * MAX_PASSES * RADIX + i];
+  pooled[i] = c;
+}
 }  // namespace
 }  // namespace dml
 
@@ -1038,6 +1046,26 @@ int dml_ood_eval_segments(uint32_t* keys, const long long* seg_stats, int32_t n_
   range_info_from_stats_kernel<<<ceil_div_i(n_seg, 256), 256, 0, stream>>>((const unsigned long long*)seg_stats, seg_len, n_seg, info);
   DML_LAUNCH_CHECK();
   return run_scan(sorted, m, ws, info, recall_level, (const unsigned long long*)seg_stats, results, nullptr, stream);
+}
+
+int dml_ood_pool_histograms(const void* seg_workspace, size_t seg_workspace_bytes, int32_t n_seg, int64_t seg_len,
+                            void* pooled_workspace, size_t pooled_workspace_bytes, int64_t pooled_len, int32_t reset,
+                            dml_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!seg_workspace || !pooled_workspace || n_seg < 0 || n_seg > 65535 || seg_len < 0 || pooled_len < 0) return DML_ERR_INVALID_ARG;
+  if (seg_len >= (1ll << 32) || pooled_len >= (1ll << 32)) return DML_ERR_INVALID_ARG;
+  const SortPlan seg_plan = make_sort_plan(n_seg > 0 ? n_seg : 1, seg_len, 0, 32);
+  const SortPlan pool_plan = make_sort_plan(1, pooled_len, 0, 32);
+  if (seg_workspace_bytes < seg_plan.off_end || pooled_workspace_bytes < pool_plan.off_end) return DML_ERR_WORKSPACE;
+  const uint32_t* sh = reinterpret_cast<const uint32_t*>(reinterpret_cast<const unsigned char*>(seg_workspace) + seg_plan.off_hist);
+  uint32_t* ph = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(pooled_workspace) + pool_plan.off_hist);
+  if (n_seg == 0 || seg_len == 0) {
+    if (reset) DML_CUDA_TRY(cudaMemsetAsync(ph, 0, (size_t)MAX_PASSES * RADIX * sizeof(uint32_t), stream));
+    return DML_OK;
+  }
+  pool_hist_kernel<<<MAX_PASSES, RADIX, 0, stream>>>(sh, n_seg, ph, reset);
+  DML_LAUNCH_CHECK();
+  return DML_OK;
 }
 
 int dml_ood_roc_fpr(const uint32_t* keys, const long long* seg_stats, int32_t n_seg, int64_t seg_len, double recall_level,

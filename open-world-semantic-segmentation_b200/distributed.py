@@ -164,27 +164,34 @@ def choose_splitters(all_samples: torch.Tensor, world: int) -> torch.Tensor:
 def pooled_measures(conf: torch.Tensor, gt: torch.Tensor, out_labels: Sequence[int] = (13,), *, group=None,
                     recall_level: float = ood.RECALL_LEVEL_DEFAULT, mode: str = "partition", ops=None,
                     workspace: Optional[ood.OodWorkspace] = None, key_base: int = ood.KEY_BASE_NONNEG,
-                    timing: bool = False):
+                    timing: bool = False, keys_and_stats=None):
     """Exact pooled (auroc, aupr, fpr, info) over the (conf, gt) pairs of ALL ranks of ``group``.
     ``conf`` must be non-negative (normalised maps); positives are gt in ``out_labels``; the ranked
-    score is -conf like anomaly/eval_ood_traditional.py:139-141.  Collective: every rank must call it."""
+    score is -conf like anomaly/eval_ood_traditional.py:139-141.  Collective: every rank must call it.
+    ``keys_and_stats`` = (packed keys int32 [n], stats int64 [>=3] = n_pos, n_nan, n_out_of_window), e.g. an
+    ``ood.KeyPool``'s ``keys`` / ``stats[0]`` filled by the per-image evaluation: the rank's key generation is skipped
+    (``conf`` / ``gt`` may then be None); the keys may be in any order."""
     if mode not in ("partition", "alltoall", "allgather"):
         raise ValueError("mode must be 'partition', 'alltoall' or 'allgather'")
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
-    ops = ops or CudaOps(conf.device, workspace)
-    dev = conf.device
+    dev = conf.device if keys_and_stats is None else keys_and_stats[0].device
+    ops = ops or CudaOps(dev, workspace)
     marks = []
 
     def mark(name):
         # CUDA-event phase boundaries on the current stream (``timing=True``; CUDA tensors only)
-        if timing and conf.is_cuda:
+        if timing and dev.type == "cuda":
             ev = torch.cuda.Event(enable_timing=True)
             ev.record(torch.cuda.current_stream(dev))
             marks.append((name, ev))
 
     mark("start")
-    keys, stats = ops.make_keys(conf, gt, out_labels, key_base)
+    if keys_and_stats is None:
+        keys, stats = ops.make_keys(conf, gt, out_labels, key_base)
+    else:
+        keys, stats = keys_and_stats
+        keys, stats = keys.contiguous().view(-1), stats.view(-1)
     mark("keygen")
     partition = mode == "partition"
     n_local = keys.numel()

@@ -48,6 +48,60 @@ class OodWorkspace:
         return cur
 
 
+class KeyPool:
+    """Pooled metric over the (score, label) pairs of many ``eval_segments`` calls -- e.g. the exact full-set
+    AUROC / AUPR / FPR@95 next to the per-image mean -- without generating or counting the ranking keys twice.
+
+    Pass the pool to every ``eval_segments(..., pool=pool)`` call of the evaluation: the call writes its packed keys
+    into the pool's next slice (the per-segment sort then runs in place there), adds its digit histograms to the
+    pooled histogram (``dml_ood_pool_histograms``) and its positive / NaN counts to the pooled stats.
+    ``evaluate()`` finally sorts and scans the whole buffer as ONE segment.  All calls must use the same
+    ``key_base`` / ``score_kind``; ``reset()`` starts the next evaluation (buffers are kept)."""
+
+    def __init__(self, capacity: int, device, workspace: Optional["OodWorkspace"] = None, histograms: bool = True):
+        self.device = torch.device(device)
+        self.capacity = int(capacity)
+        if not 0 < self.capacity < (1 << 32):
+            raise ValueError("KeyPool capacity must lie in (0, 2^32)")
+        self.ws = workspace or OodWorkspace(self.device)
+        self.keys = torch.empty(self.capacity, dtype=torch.int32, device=self.device)   # u32 bit patterns
+        # histograms=False: only the keys and counts are pooled (multi-GPU: the keys are re-partitioned across ranks
+        # by distributed.pooled_measures(keys_and_stats=...), so a local pooled histogram would be of no use)
+        self.scratch = self.ws.get("pool_scratch", lib().dml_ood_workspace_bytes(1, self.capacity)) if histograms else None
+        self.stats = torch.zeros(1, 4, dtype=torch.int64, device=self.device)
+        self.reset()
+
+    def reset(self):
+        self.n = 0
+        self.signature = None
+        self.stats.zero_()
+
+    def _take(self, n: int, signature) -> torch.Tensor:
+        if self.n + n > self.capacity:
+            raise ValueError(f"KeyPool overflow: {self.n} + {n} > capacity {self.capacity}")
+        if self.signature is None:
+            self.signature = signature
+        elif self.signature != signature:
+            raise ValueError("all eval_segments calls of one KeyPool must share key_base and score_kind")
+        view = self.keys[self.n:self.n + n]
+        self.n += n
+        return view
+
+    def evaluate(self, recall_level: float = RECALL_LEVEL_DEFAULT):
+        """(results [1,7] float64, stats [1,4] int64) device tensors of the pooled segment, like ``eval_segments``.
+        The pool must be full (``capacity`` keys): the pooled histogram slot belongs to that segment length."""
+        if self.scratch is None:
+            raise ValueError("KeyPool(histograms=False) only collects keys; evaluate them with distributed.pooled_measures")
+        if self.n != self.capacity:
+            raise ValueError(f"KeyPool holds {self.n} keys, capacity is {self.capacity}: size the pool to the evaluation")
+        results = self.ws.get("pool_results", 8 * OOD_RESULT_WORDS).view(torch.float64)[:OOD_RESULT_WORDS].view(1, OOD_RESULT_WORDS)
+        with torch.cuda.device(self.device):
+            check(lib().dml_ood_eval_segments(ptr(self.keys), ptr(self.stats), 1, self.capacity, recall_level,
+                                              ptr(self.scratch), self.scratch.numel(), 1, ptr(results),
+                                              stream_ptr(self.device)), "dml_ood_eval_segments")
+        return results, self.stats
+
+
 def _raise_on_bad_stats(stats: np.ndarray, what: str):
     if (stats[:, 1] > 0).any():
         raise ValueError("Input contains NaN.")           # sklearn's validation in the reference path
@@ -61,7 +115,7 @@ def eval_segments(values: torch.Tensor, n_seg: int, seg_len: int, *, gt: Optiona
                   conf_out: Optional[torch.Tensor] = None, recall_level: float = RECALL_LEVEL_DEFAULT,
                   workspace: Optional[OodWorkspace] = None, msp: Optional[torch.Tensor] = None,
                   msp_norm_out: Optional[torch.Tensor] = None, mix_out: Optional[torch.Tensor] = None,
-                  lam: float = 50.0, thr: float = 0.2):
+                  lam: float = 50.0, thr: float = 0.2, pool: Optional[KeyPool] = None):
     """Evaluate ``n_seg`` independent segments of ``seg_len`` (score, label) pairs each.
 
     values: flat fp32 CUDA tensor (n_seg*seg_len): a ``conf`` map ranked as score = -conf
@@ -72,6 +126,8 @@ def eval_segments(values: torch.Tensor, n_seg: int, seg_len: int, *, gt: Optiona
             normalised value (slot 0: eds, 1: msp) and can store it to ``conf_out``.
     msp / msp_norm_out / mix_out: fused score maps (slot 0 only): MMSP = normalised ``msp`` and the
             EDS/MMSP mix (anomaly/eval_ood_traditional.py:434-435,447-448) written in the same pass.
+    pool:   a ``KeyPool`` collecting the keys / digit histograms / counts of this call for a later pooled
+            evaluation over all calls (``pool.evaluate()``).
     Returns (results, stats): device tensors -- results float64 [n_seg,7] viewed as
     (auroc, aupr, fpr, n_pos, n_neg, n_nan, n_groups; the last four are int64 bit patterns),
     stats int64 [n_seg,4] = (n_pos, n_nan, n_out_of_window, 0).  No host synchronisation.
@@ -83,7 +139,7 @@ def eval_segments(values: torch.Tensor, n_seg: int, seg_len: int, *, gt: Optiona
         raise ValueError("values must be float32 with n_seg*seg_len elements")
     ws = workspace or OodWorkspace(dev)
     n = n_seg * seg_len
-    keys = ws.get("keys", 4 * n)
+    keys = ws.get("keys", 4 * n) if pool is None else pool._take(n, (int(key_base), int(score_kind)))
     stats = ws.get("stats", 32 * max(n_seg, 1)).view(torch.int64)[: 4 * n_seg].view(n_seg, 4)
     results = ws.get("results", 8 * OOD_RESULT_WORDS * max(n_seg, 1)).view(torch.float64)[: OOD_RESULT_WORDS * n_seg]
     results = results.view(n_seg, OOD_RESULT_WORDS)
@@ -112,7 +168,7 @@ def eval_segments(values: torch.Tensor, n_seg: int, seg_len: int, *, gt: Optiona
     # -1 ms per 1.38 G pairs for 50-image batches, +1.4 ms for one long segment, hence the n_seg rule;
     # DML_FUSED_HIST=0 / 1 forces the separate / fused form)
     fh = os.environ.get("DML_FUSED_HIST", "")
-    fused_hist = n > 0 and (fh == "1" or (fh != "0" and n_seg >= 4))
+    fused_hist = n > 0 and (fh == "1" or (fh != "0" and n_seg >= 4) or pool is not None)
     with torch.cuda.device(dev):
         s = stream_ptr(dev)
         check(lib().dml_ood_keygen(ptr(values), ptr(minmax), minmax_slot, ptr(conf_out), ptr(gt_u8), ptr(gt_i64),
@@ -120,6 +176,13 @@ def eval_segments(values: torch.Tensor, n_seg: int, seg_len: int, *, gt: Optiona
                                    n_seg, seg_len, ptr(keys), ptr(stats), ptr(msp), ptr(msp_norm_out), ptr(mix_out),
                                    lam, thr, ptr(scratch) if fused_hist else None, scratch.numel() if fused_hist else 0, s),
               "dml_ood_keygen")
+        if pool is not None and n > 0:
+            # between key-gen and the sort the workspace holds the raw per-segment digit counts
+            if pool.scratch is not None:
+                check(lib().dml_ood_pool_histograms(ptr(scratch), scratch.numel(), n_seg, seg_len, ptr(pool.scratch),
+                                                    pool.scratch.numel(), pool.capacity, 1 if pool.n == n else 0, s),
+                      "dml_ood_pool_histograms")
+            pool.stats += stats.sum(dim=0, keepdim=True)
         check(lib().dml_ood_eval_segments(ptr(keys), ptr(stats), n_seg, seg_len, recall_level, ptr(scratch),
                                           scratch.numel(), 1 if fused_hist else 0, ptr(results), s), "dml_ood_eval_segments")
     return results, stats

@@ -24,6 +24,7 @@ def _free_port():
 def _make_shard(rank, case):
     rng = np.random.default_rng(100 + rank)
     n = {0: 5000, 1: 7001, 2: 123}[rank]
+    case = case.split("+")[0]
     if case == "empty_rank" and rank == 1:
         n = 0
     conf = rng.random(n).astype(np.float32)
@@ -45,7 +46,18 @@ def _worker(rank, world, port, case, mode, q):
         from dml_b200 import distributed as D
         from tests.np_ops import NumpyOps
         conf, gt = _make_shard(rank, case)
-        a, p, f, info = D.pooled_measures(torch.from_numpy(conf), torch.from_numpy(gt), (13,), mode=mode, ops=NumpyOps())
+        if case.endswith("+keys"):
+            # keys handed over by the per-image evaluation (an ood.KeyPool on the GPU): already generated, and left
+            # sorted inside every 1000-pair "image" by the per-image sorts
+            ops = NumpyOps()
+            keys, stats = ops.make_keys(torch.from_numpy(conf), torch.from_numpy(gt), (13,), 0x80000000)
+            k = keys.numpy().view(np.uint32).copy()
+            for s0 in range(0, k.size, 1000):
+                k[s0:s0 + 1000].sort()
+            a, p, f, info = D.pooled_measures(None, None, (13,), mode=mode, ops=ops,
+                                              keys_and_stats=(torch.from_numpy(k.view(np.int32)), stats))
+        else:
+            a, p, f, info = D.pooled_measures(torch.from_numpy(conf), torch.from_numpy(gt), (13,), mode=mode, ops=NumpyOps())
         vals = torch.tensor([[0.5 + 0.1 * rank, 0.2, 0.3], [float("nan")] * 3, [0.7, 0.4, 0.1]], dtype=torch.float64)
         mean = D.mean_of_per_image(vals)
         conf_m = torch.full((3, 3), rank + 1, dtype=torch.int64)
@@ -58,7 +70,8 @@ def _worker(rank, world, port, case, mode, q):
 @pytest.mark.parametrize("world,case,mode", [(2, "plain", "alltoall"), (2, "ties", "alltoall"), (2, "ties", "allgather"),
                                              (3, "skewed", "alltoall"), (3, "empty_rank", "allgather"), (2, "empty_rank", "alltoall"),
                                              (2, "plain", "partition"), (2, "ties", "partition"), (3, "skewed", "partition"),
-                                             (3, "empty_rank", "partition")])
+                                             (3, "empty_rank", "partition"), (2, "ties+keys", "partition"),
+                                             (3, "empty_rank+keys", "partition"), (2, "plain+keys", "allgather")])
 def test_pooled_measures_gloo(world, case, mode):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()

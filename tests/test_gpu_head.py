@@ -72,6 +72,70 @@ def test_head_identity_prototypes(k, h, w):
     _check_head(x, O.make_centers(k), k)
 
 
+def _check_lean_head(x_cpu, K, magnitude=3.0, exclude_back=False, clamp=400.0):
+    """The scoring configuration (no logits returned) of the mu = m*I fast path never forms a per-class
+    distance: EDS from the closed form (D-1)*S + sum_k (x_k-m)^2, label = first extremal channel,
+    max-softmax from 2*m*x_k.  Same bars as the logits-returning path."""
+    import dml_b200
+    x = x_cpu.cuda()
+    centers = O.make_centers(K, magnitude)
+    out = dml_b200.dml_head(x, magnitude=magnitude, want_logits=False, label_dtype=torch.int64, want_maxlogit=True,
+                            want_eds=True, eds_clamp=clamp, want_msp=True, want_minmax=True, exclude_back=exclude_back)
+    out8 = dml_b200.dml_head(x, magnitude=magnitude, want_logits=False, label_dtype=torch.uint8, want_eds=True,
+                             eds_clamp=clamp, exclude_back=exclude_back)
+    full = dml_b200.dml_head(x, magnitude=magnitude, want_logits=True, label_dtype=torch.int64, want_maxlogit=True,
+                             want_eds=True, eds_clamp=clamp, want_msp=True, exclude_back=exclude_back)
+    torch.cuda.synchronize()
+    z_ref = O.distance_logits(x_cpu, centers)
+    z64 = O.distance_logits_f64(x_cpu, centers)
+    lab = out.label.cpu()
+    diff = lab != z_ref.max(dim=1)[1]
+    assert not (diff & ~_near_tie_mask(z_ref)).any(), "label mismatch away from ties"
+    # exact-arithmetic label: the nearest prototype of m*I is the first largest (m > 0) / smallest (m < 0) channel
+    assert torch.equal(lab, (x_cpu if magnitude >= 0 else -x_cpu).max(dim=1)[1])
+    assert torch.equal(out8.label.cpu().long(), lab)
+    assert torch.equal(out8.eds, out.eds)
+    first = 1 if exclude_back and K > 1 else 0
+    zs = z_ref[:, first:]
+    eds_ref = -(zs.sum(dim=1))
+    eds_ref = torch.where(eds_ref >= clamp, torch.full_like(eds_ref, clamp), eds_ref) if clamp > 0 else eds_ref
+    np.testing.assert_allclose(out.eds.cpu().numpy(), eds_ref.numpy(), rtol=1e-5)
+    np.testing.assert_allclose(out.maxlogit.cpu().numpy(), zs.max(dim=1)[0].numpy(), rtol=1e-5)
+    np.testing.assert_allclose(out.maxlogit.cpu().numpy(), z64[:, first:].max(dim=1)[0].numpy(), rtol=3e-6)
+    msp64 = torch.softmax(z64[:, first:], dim=1).max(dim=1)[0]
+    np.testing.assert_allclose(out.msp.cpu().numpy(), msp64.numpy(), rtol=2e-6)
+    # against the logits-returning instantiation of the same kernel
+    np.testing.assert_allclose(out.eds.cpu().numpy(), full.eds.cpu().numpy(), rtol=2e-6)
+    np.testing.assert_allclose(out.msp.cpu().numpy(), full.msp.cpu().numpy(), rtol=1e-6)
+    np.testing.assert_allclose(out.maxlogit.cpu().numpy(), full.maxlogit.cpu().numpy(), rtol=2e-6)
+    mm = out.minmax.cpu()
+    B = x.shape[0]
+    e, m = out.eds.cpu().view(B, -1), out.msp.cpu().view(B, -1)
+    assert torch.equal(mm[:, 0], e.min(1)[0]) and torch.equal(mm[:, 1], e.max(1)[0])
+    assert torch.equal(mm[:, 2], m.min(1)[0]) and torch.equal(mm[:, 3], m.max(1)[0])
+
+
+@pytest.mark.parametrize("k,h,w", [(13, 72, 128), (16, 64, 96), (17, 48, 64), (19, 40, 52), (13, 38, 67), (3, 9, 7), (1, 5, 4),
+                                   (2, 6, 10), (32, 16, 24), (24, 20, 20), (8, 32, 32)])
+def test_lean_head_identity_prototypes(k, h, w):
+    x, _ = streethazards_like(2, h, w, k=k, sigma=0.7, ood_label=k, seed=k + h)
+    _check_lean_head(x, k)
+
+
+def test_lean_head_tight_clusters_exclude_back_negative_magnitude():
+    x, _ = streethazards_like(2, 64, 64, k=13, sigma=0.1, seed=5)
+    _check_lean_head(x, 13)                                   # own-class distance ~0.03 while ||x||^2 ~ 9
+    _check_lean_head(x, 13, exclude_back=True, clamp=0.0)
+    x2, _ = streethazards_like(1, 40, 64, k=13, seed=9)
+    _check_lean_head(x2, 13, exclude_back=True)
+    _check_lean_head(-x2, 13, magnitude=-3.0)                 # m < 0: the nearest prototype is the smallest channel
+    # exact ties between channels: first index wins, like torch.max on the logits
+    x3 = x2.clone()
+    x3[:, 5] = x3[:, 2]
+    x3[:, 0, ::2] = x3[:, 2, ::2].clone()
+    _check_lean_head(x3, 13)
+
+
 def test_head_tight_clusters_no_cancellation():
     """sigma = 0.1 puts own-class distances at ~0.03..0.1 while ||x||^2 ~ 9: an expanded-form kernel
     loses 1e-4 relative here (hard part 2); the leave-one-out form must not."""

@@ -105,6 +105,53 @@ def test_fused_normalisation_keygen():
         np.testing.assert_allclose(mix_out[s].cpu().numpy(), O.score_mix(conf, mmsp), rtol=1e-5, atol=1e-6)
 
 
+@pytest.mark.parametrize("batches,seg_len", [([4, 4, 2], 4096), ([1, 3], 4097), ([5], 70001), ([2, 2, 2, 1], 12290), ([3, 1], 5)])
+def test_key_pool_equals_separate_pooled_evaluation(batches, seg_len):
+    """ood.KeyPool: the pooled metric computed from the keys / digit histograms the per-segment calls leave behind
+    is bit-identical to a second, separate evaluation of the concatenated maps as one segment (and equals the
+    oracle); the per-segment results are unchanged by the pooling."""
+    from dml_b200 import ood
+    n_seg = sum(batches)
+    rng = np.random.default_rng(n_seg * 977 + seg_len)
+    raw = (rng.random((n_seg, seg_len)) * 500).astype(np.float32)
+    raw[0] = np.round(raw[0] / 10) * 10                 # heavy ties
+    raw[raw >= 400] = 400                               # clamp plateau shared by all segments
+    gt = rng.integers(0, 14, (n_seg, seg_len)).astype(np.uint8)
+    gt[rng.random((n_seg, seg_len)) < 0.8] = 3
+    mm = np.zeros((n_seg, 4), np.float32)
+    mm[:, 0], mm[:, 1] = raw.min(1), raw.max(1)
+    raw_d, gt_d, mm_d = torch.from_numpy(raw).cuda(), torch.from_numpy(gt).cuda(), torch.from_numpy(mm).cuda()
+    conf_d = torch.empty(n_seg, seg_len, device="cuda")
+    pool = ood.KeyPool(n_seg * seg_len, "cuda")
+    for rep in range(2):                                # second round: reset() reuses the buffers
+        pool.reset()
+        per_seg, s0 = [], 0
+        for nb in batches:
+            res, stats = ood.eval_segments(raw_d[s0:s0 + nb], nb, seg_len, gt=gt_d[s0:s0 + nb], out_labels=(13,),
+                                           minmax=mm_d[s0:s0 + nb], minmax_slot=0, conf_out=conf_d[s0:s0 + nb], pool=pool)
+            per_seg.append(ood.results_to_host(res, stats)[0])
+            s0 += nb
+        pres, pstats = pool.evaluate()
+        pooled, pcounts = ood.results_to_host(pres, pstats)
+        sres, sstats = ood.eval_segments(conf_d.view(-1), 1, n_seg * seg_len, gt=gt_d.view(-1), out_labels=(13,))
+        separate, scounts = ood.results_to_host(sres, sstats)
+        np.testing.assert_array_equal(pooled, separate)
+        np.testing.assert_array_equal(pcounts, scounts)
+        conf = np.stack([O.normalization(raw[s]) for s in range(n_seg)])
+        per_seg = np.concatenate(per_seg)
+        for got, c, g in [(pooled[0], conf.reshape(-1), gt.reshape(-1))] + [(per_seg[s], conf[s], gt[s]) for s in range(n_seg)]:
+            ref = O.eval_ood_measure(c, g.astype(np.int64), (13,))
+            if ref is None:                             # single-class segment
+                assert np.isnan(got).all()
+            else:
+                np.testing.assert_allclose(got, ref, rtol=0, atol=1e-12)
+    with pytest.raises(ValueError):                     # a partly filled pool cannot be evaluated
+        pool.reset()
+        pool.evaluate()
+    with pytest.raises(ValueError):                     # overflow
+        ood.eval_segments(raw_d, n_seg, seg_len, gt=gt_d, out_labels=(13,), pool=ood.KeyPool(seg_len, "cuda"))
+
+
 def test_large_single_segment_properties():
     """2^24+3 pairs: AUROC(score) + AUROC(-score) == 1 with ties counted half, positives/negatives swap symmetry."""
     from dml_b200 import ood
