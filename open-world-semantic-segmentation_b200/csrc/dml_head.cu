@@ -163,7 +163,13 @@ int dml_head_forward(const dml_head_params* p, dml_stream_t stream_) {
     minmax_init_kernel<<<ceil_div_i(n4, 256), 256, 0, stream>>>(a.minmax, n4);
     DML_LAUNCH_CHECK();
   }
-  const bool extra = a.n_novel > 0 || a.feat != nullptr || a.novel_dist != nullptr || a.logits != nullptr;
+  bool extra = a.n_novel > 0 || a.feat != nullptr || a.novel_dist != nullptr || a.logits != nullptr;
+  // DML_HEAD_LEAN=0: score mu = m*I inputs through the per-class-distance instantiation instead of the closed-form
+  // lean path (cross-check / A-B timing knob; read per call, no state kept)
+  if (mode == HEAD_IDENT && !extra) {
+    const char* e = getenv("DML_HEAD_LEAN");
+    if (e && e[0] == '0') extra = true;
+  }
   int vec = pick_vec(p, hw);
   if (extra && vec > 2) vec = 2;
   const int D = p->D;

@@ -13,14 +13,16 @@
 //   AUPR  = sum_g pos_g * tps_g / (tps_g + fps_g) / P
 //   FPR   = fps_{g*} / N,  g* = argmin_g |tps_g / P - recall| over groups with tps_{g-1} < P,
 //           ties -> the LATER group (anom_utils.py:57-65 scans from the lowest threshold down).
+#include <cstdlib>
+
 #include "ood_sort.cuh"
+#include "ood_scan_thread.cuh"
 
 namespace dml {
 
 namespace {
 
 constexpr int SCAN_THREADS = 256;
-constexpr int SCAN_ITEMS = 16;
 constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
 constexpr int SCAN_WARPS = SCAN_THREADS / 32;
 
@@ -262,17 +264,7 @@ __global__ void keystats_init_kernel(unsigned long long* s, int n_seg) {
 // ---------------------------------------------------------------------------------------------
 // segmented scan over score groups
 // ---------------------------------------------------------------------------------------------
-struct Agg {  // tile-local counts (<= SCAN_TILE)
-  unsigned pos, spos, slen, head;
-};
-__device__ __forceinline__ Agg agg_combine(const Agg& a, const Agg& b) {
-  Agg r;
-  r.pos = a.pos + b.pos;
-  r.spos = b.head ? b.spos : a.spos + b.spos;
-  r.slen = b.head ? b.slen : a.slen + b.slen;
-  r.head = a.head | b.head;
-  return r;
-}
+// Agg / Carry / TilePartial and the per-thread mask arithmetic: ood_scan_thread.cuh
 __device__ __forceinline__ Agg agg_shfl_up(const Agg& a, int o) {
   Agg r;
   r.pos = __shfl_up_sync(0xffffffffu, a.pos, o);
@@ -280,48 +272,6 @@ __device__ __forceinline__ Agg agg_shfl_up(const Agg& a, int o) {
   r.slen = __shfl_up_sync(0xffffffffu, a.slen, o);
   r.head = __shfl_up_sync(0xffffffffu, a.head, o);
   return r;
-}
-
-struct Carry {  // running state across tiles (64-bit)
-  unsigned long long pos, spos, slen;
-};
-// Per-tile / per-range partial result (10 x 8 bytes; the layout is part of the C ABI, see
-// dml_ood_scan_range).  FPR candidates are kept in integers: with T* = the largest tps whose
-// float64 recall tps/P is <= recall_level, |tps/P - recall_level| is non-increasing up to T* and
-// non-decreasing after it, so the reference's argmin (ties -> later group) is one of
-//   a = the LAST group with tps <= T*,   b = the smallest tps > T*, latest group having it.
-struct TilePartial {
-  unsigned long long auroc_num;
-  double ap_sum;
-  long long a_idx, a_tps, a_fps;   // a_idx = -1: none
-  long long b_tps, b_idx, b_fps;   // b_tps = LLONG_MAX: none
-  long long n_groups;
-  long long reserved;
-};
-constexpr long long NO_B = 0x7fffffffffffffffll;
-
-__device__ __forceinline__ void partial_init(TilePartial& t) {
-  t.auroc_num = 0ull; t.ap_sum = 0.0;
-  t.a_idx = -1; t.a_tps = 0; t.a_fps = 0;
-  t.b_tps = NO_B; t.b_idx = -1; t.b_fps = 0;
-  t.n_groups = 0; t.reserved = 0;
-}
-__device__ __forceinline__ void partial_merge(TilePartial& a, const TilePartial& b) {
-  a.auroc_num += b.auroc_num;
-  a.ap_sum += b.ap_sum;
-  a.n_groups += b.n_groups;
-  if (b.a_idx > a.a_idx) { a.a_idx = b.a_idx; a.a_tps = b.a_tps; a.a_fps = b.a_fps; }
-  if (b.b_tps < a.b_tps || (b.b_tps == a.b_tps && b.b_idx > a.b_idx)) { a.b_tps = b.b_tps; a.b_idx = b.b_idx; a.b_fps = b.b_fps; }
-}
-// largest integer t in [0, P] with (double)t / (double)P <= r  (float64 division, like NumPy's recall)
-__device__ __forceinline__ long long recall_threshold(long long P, double r) {
-  if (P <= 0) return 0;
-  const double dP = (double)P;
-  double g = floor(r * dP);
-  long long t = g < 0.0 ? 0 : (g > dP ? P : (long long)g);
-  while (t < P && (double)(t + 1) / dP <= r) ++t;
-  while (t > 0 && (double)t / dP > r) --t;
-  return t;
 }
 
 struct RangeInfo {  // device-resident description of one scan range (segment)
@@ -345,11 +295,19 @@ __device__ __forceinline__ int pad_idx(int i) { return i + (i >> 4); }
 __device__ __forceinline__ void load_tile(const uint32_t* __restrict__ keys, long long n, long long tile_off,
                                           uint32_t* s_keys /*[SCAN_TILE + SCAN_TILE/16 + 2]*/, TileKeys& tk) {
   const int tid = threadIdx.x;
+  if (tile_off + SCAN_TILE <= n) {
+    // full tile (all but the last tile of a segment): no bounds tests, immediate offsets
+    const uint32_t* src = keys + tile_off + tid;
+    uint32_t* dst = s_keys + tid + (tid >> 4);
 #pragma unroll
-  for (int j = 0; j < SCAN_ITEMS; ++j) {
-    const int i = j * SCAN_THREADS + tid;
-    const long long g = tile_off + i;
-    s_keys[pad_idx(i)] = g < n ? keys[g] : 0u;
+    for (int j = 0; j < SCAN_ITEMS; ++j) dst[j * (SCAN_THREADS + SCAN_THREADS / 16)] = src[j * SCAN_THREADS];
+  } else {
+#pragma unroll
+    for (int j = 0; j < SCAN_ITEMS; ++j) {
+      const int i = j * SCAN_THREADS + tid;
+      const long long g = tile_off + i;
+      s_keys[pad_idx(i)] = g < n ? keys[g] : 0u;
+    }
   }
   __shared__ uint32_t s_edge[2];
   if (tid == 0) {
@@ -384,7 +342,9 @@ __device__ __forceinline__ Agg thread_aggregate(const TileKeys& tk, long long n,
   return a;
 }
 
-// phase 1: per-tile aggregate
+// phase 1: per-tile aggregate.  BITS: the run's aggregate from its bit masks (ood_scan_thread.cuh); !BITS: the
+// original one-step-per-key state machine, kept selectable (DML_SCAN_BITS=0) as the cross-check of the mask form.
+template <bool BITS>
 __global__ void __launch_bounds__(SCAN_THREADS) scan_agg_kernel(const uint32_t* __restrict__ keys, long long seg_len,
                                                                 int tiles_per_seg, Agg* __restrict__ tile_agg) {
   __shared__ uint32_t s_keys[SCAN_TILE + SCAN_TILE / 16 + 2];
@@ -394,7 +354,10 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_agg_kernel(const uint32_t* 
   const long long tile_off = (long long)tile * SCAN_TILE;
   TileKeys tk;
   load_tile(k, seg_len, tile_off, s_keys, tk);
-  Agg a = thread_aggregate(tk, seg_len, tile_off + (long long)tid * SCAN_ITEMS);
+  const long long first = tile_off + (long long)tid * SCAN_ITEMS;
+  Agg a;
+  if constexpr (BITS) a = run_aggregate(run_masks(tk.k, tk.prev, tk.has_prev, tk.next, first, seg_len));
+  else a = thread_aggregate(tk, seg_len, first);
   // ordered inclusive warp scan, keep the last lane's value
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
@@ -412,11 +375,6 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_agg_kernel(const uint32_t* 
 
 // phase 2: exclusive scan of the tile aggregates of each segment -> carry-in per tile
 constexpr int CARRY_THREADS = 1024;
-__device__ __forceinline__ void carry_apply(Carry& c, unsigned& chead, const Agg& b) {
-  c.pos += b.pos;
-  if (b.head) { c.spos = b.spos; c.slen = b.slen; chead = 1; }
-  else { c.spos += b.spos; c.slen += b.slen; }
-}
 struct CarryH { Carry c; unsigned head; };
 __device__ __forceinline__ CarryH carryh_combine(const CarryH& a, const CarryH& b) {
   CarryH r;
@@ -507,8 +465,9 @@ __global__ void __launch_bounds__(CARRY_THREADS) scan_chunk_prefix_kernel(CarryH
   if (tid < chunks) chunk_state[(size_t)seg * chunks + tid] = run;
 }
 
-// phase 3: per-tile group contributions
-__global__ void __launch_bounds__(SCAN_THREADS, 3) scan_apply_kernel(const uint32_t* __restrict__ keys, long long seg_len,
+// phase 3: per-tile group contributions (BITS: see scan_agg_kernel)
+template <bool BITS>
+__global__ void __launch_bounds__(SCAN_THREADS, BITS ? 4 : 3) scan_apply_kernel(const uint32_t* __restrict__ keys, long long seg_len,
                                                                   int tiles_per_seg, const Carry* __restrict__ tile_carry,
                                                                   const RangeInfo* __restrict__ info, double recall_level,
                                                                   TilePartial* __restrict__ partials) {
@@ -525,7 +484,14 @@ __global__ void __launch_bounds__(SCAN_THREADS, 3) scan_apply_kernel(const uint3
   TileKeys tk;
   load_tile(k, seg_len, tile_off, s_keys, tk);   // contains the __syncthreads that publishes s_tstar
   const long long tstar = s_tstar;
-  const Agg mine = thread_aggregate(tk, seg_len, first);
+  RunMasks rm = {};
+  Agg mine;
+  if constexpr (BITS) {
+    rm = run_masks(tk.k, tk.prev, tk.has_prev, tk.next, first, seg_len);
+    mine = run_aggregate(rm);
+  } else {
+    mine = thread_aggregate(tk, seg_len, first);
+  }
   // exclusive block scan of the thread aggregates
   Agg incl = mine;
 #pragma unroll
@@ -555,13 +521,20 @@ __global__ void __launch_bounds__(SCAN_THREADS, 3) scan_apply_kernel(const uint3
   const int rem_local = clamp_local(Ptot - base_P);           // tps_{g-1} < Ptot <=>  Pl_start < rem_local
   const bool open_valid = (base_P - open_pos) < Ptot;         // same test for the group carried in
 
+  unsigned long long auroc;
+  double ap;
+  int a_j = -1, a_Pl = 0, b_j = -1, b_Pl = 0, ngroups = 0;
+  if constexpr (BITS) {
+    const RunContribution rc = run_contribution(rm, base_P, open_pos, open_len, Ptot, first_idx, t_local, rem_local);
+    auroc = rc.auroc; ap = rc.ap_sum; ngroups = rc.n_groups;
+    a_j = rc.a_j; a_Pl = rc.a_Pl; b_j = rc.b_j; b_Pl = rc.b_Pl;
+  } else {
   TilePartial acc;
   partial_init(acc);
   unsigned long long neg_P = 0ull, tie = 0ull;   // sum over negatives of Pl ; sum over mixed groups of neg_g * pos_g
   int n_neg = 0;
   int Pl = 0, ls = 0, ll = 0, Pl_start = 0;
   bool in_thread = false;                        // current group started inside my run
-  int a_j = -1, a_Pl = 0, b_j = -1, b_Pl = 0, ngroups = 0;
 
   bool head = !tk.has_prev || ((tk.k[0] >> 1) != (tk.prev >> 1));
 #pragma unroll
@@ -600,8 +573,9 @@ __global__ void __launch_bounds__(SCAN_THREADS, 3) scan_apply_kernel(const uint3
   }
   // ---- block reduction.  Sums: fixed-order shuffles.  FPR candidates: the winning thread is found with one
   //      32-bit warp reduction on a tile-local key, only the winner materialises the 64-bit tuple. ----------
-  unsigned long long auroc = 2ull * ((unsigned long long)n_neg * (unsigned long long)base_P + neg_P) + tie;
-  double ap = acc.ap_sum;
+  auroc = 2ull * ((unsigned long long)n_neg * (unsigned long long)base_P + neg_P) + tie;
+  ap = acc.ap_sum;
+  }  // !BITS
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     auroc += __shfl_down_sync(0xffffffffu, auroc, o);
@@ -902,7 +876,11 @@ int run_scan(const uint32_t* sorted, const MetricsPlan& m, unsigned char* ws, co
   Carry* carry = reinterpret_cast<Carry*>(ws + m.off_carry);
   TilePartial* partial = reinterpret_cast<TilePartial*>(ws + m.off_partial);
   dim3 grid((unsigned)m.tiles_per_seg, (unsigned)m.sort.n_seg);
-  scan_agg_kernel<<<grid, SCAN_THREADS, 0, stream>>>(sorted, m.sort.seg_len, m.tiles_per_seg, agg);
+  // DML_SCAN_BITS=0 selects the original per-key state machine (cross-check / A-B timing); read per call, no state kept
+  const char* sb = getenv("DML_SCAN_BITS");
+  const bool bits = !(sb && sb[0] == '0');
+  if (bits) scan_agg_kernel<true><<<grid, SCAN_THREADS, 0, stream>>>(sorted, m.sort.seg_len, m.tiles_per_seg, agg);
+  else scan_agg_kernel<false><<<grid, SCAN_THREADS, 0, stream>>>(sorted, m.sort.seg_len, m.tiles_per_seg, agg);
   DML_LAUNCH_CHECK();
   CarryH* chunk_state = reinterpret_cast<CarryH*>(ws + m.off_chunk_state);
   TilePartial* chunk_partial = reinterpret_cast<TilePartial*>(ws + m.off_chunk_partial);
@@ -917,7 +895,8 @@ int run_scan(const uint32_t* sorted, const MetricsPlan& m, unsigned char* ws, co
     scan_carry_kernel<0><<<m.sort.n_seg, CARRY_THREADS, 0, stream>>>(agg, m.tiles_per_seg, m.tiles_per_seg, 1, info, chunk_state, carry);
     DML_LAUNCH_CHECK();
   }
-  scan_apply_kernel<<<grid, SCAN_THREADS, 0, stream>>>(sorted, m.sort.seg_len, m.tiles_per_seg, carry, info, recall_level, partial);
+  if (bits) scan_apply_kernel<true><<<grid, SCAN_THREADS, 0, stream>>>(sorted, m.sort.seg_len, m.tiles_per_seg, carry, info, recall_level, partial);
+  else scan_apply_kernel<false><<<grid, SCAN_THREADS, 0, stream>>>(sorted, m.sort.seg_len, m.tiles_per_seg, carry, info, recall_level, partial);
   DML_LAUNCH_CHECK();
   if (m.chunks > 1) {
     // level 1: chunk partials (fixed order inside a chunk); level 2: the chunk partials of each segment

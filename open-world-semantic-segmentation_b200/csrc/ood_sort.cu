@@ -11,6 +11,13 @@ __device__ __forceinline__ unsigned lanemask_lt() {
   return m;
 }
 
+template <typename T>
+__device__ __forceinline__ T* opaque_ptr(T* p) {
+  unsigned long long v = (unsigned long long)p;
+  asm volatile("" : "+l"(v));
+  return (T*)v;
+}
+
 // look-back words: gpu-scope relaxed accesses (served by L2), not the system-scope ones `volatile` emits
 __device__ __forceinline__ uint32_t ld_relaxed(const uint32_t* p) {
   uint32_t v;
@@ -42,22 +49,26 @@ __device__ __forceinline__ unsigned match_digit8(uint32_t d, bool valid) {
   return valid ? peers : 0u;
 }
 
-// Peer mask for one 8-bit digit in exactly 4 SASS instructions per bit (test bit -> predicate, VOTE,
-// predicated NOT, AND); nvcc's own code for the C++ form above spends 6.
+// Peer mask for one 8-bit digit: per bit a predicate test, VOTE and a predicated NOT; the eight terms are folded with
+// three-input LOP3s (a & b & c), four instead of seven ANDs.  nvcc's own code for the C++ form above spends 6 per bit.
 __device__ __forceinline__ unsigned match8_full(uint32_t d) {
   unsigned peers;
   asm volatile(
       "{\n"
       " .reg .pred p;\n"
-      " .reg .b32 v, t;\n"
+      " .reg .b32 a, b, t;\n"
       " and.b32 t, %1, 1;   setp.ne.u32 p, t, 0; vote.sync.ballot.b32 %0, p, 0xffffffff; @!p not.b32 %0, %0;\n"
-      " and.b32 t, %1, 2;   setp.ne.u32 p, t, 0; vote.sync.ballot.b32 v, p, 0xffffffff; @!p not.b32 v, v; and.b32 %0, %0, v;\n"
-      " and.b32 t, %1, 4;   setp.ne.u32 p, t, 0; vote.sync.ballot.b32 v, p, 0xffffffff; @!p not.b32 v, v; and.b32 %0, %0, v;\n"
-      " and.b32 t, %1, 8;   setp.ne.u32 p, t, 0; vote.sync.ballot.b32 v, p, 0xffffffff; @!p not.b32 v, v; and.b32 %0, %0, v;\n"
-      " and.b32 t, %1, 16;  setp.ne.u32 p, t, 0; vote.sync.ballot.b32 v, p, 0xffffffff; @!p not.b32 v, v; and.b32 %0, %0, v;\n"
-      " and.b32 t, %1, 32;  setp.ne.u32 p, t, 0; vote.sync.ballot.b32 v, p, 0xffffffff; @!p not.b32 v, v; and.b32 %0, %0, v;\n"
-      " and.b32 t, %1, 64;  setp.ne.u32 p, t, 0; vote.sync.ballot.b32 v, p, 0xffffffff; @!p not.b32 v, v; and.b32 %0, %0, v;\n"
-      " and.b32 t, %1, 128; setp.ne.u32 p, t, 0; vote.sync.ballot.b32 v, p, 0xffffffff; @!p not.b32 v, v; and.b32 %0, %0, v;\n"
+      " and.b32 t, %1, 2;   setp.ne.u32 p, t, 0; vote.sync.ballot.b32 a, p, 0xffffffff; @!p not.b32 a, a;\n"
+      " and.b32 t, %1, 4;   setp.ne.u32 p, t, 0; vote.sync.ballot.b32 b, p, 0xffffffff; @!p not.b32 b, b;\n"
+      " lop3.b32 %0, %0, a, b, 0x80;\n"
+      " and.b32 t, %1, 8;   setp.ne.u32 p, t, 0; vote.sync.ballot.b32 a, p, 0xffffffff; @!p not.b32 a, a;\n"
+      " and.b32 t, %1, 16;  setp.ne.u32 p, t, 0; vote.sync.ballot.b32 b, p, 0xffffffff; @!p not.b32 b, b;\n"
+      " lop3.b32 %0, %0, a, b, 0x80;\n"
+      " and.b32 t, %1, 32;  setp.ne.u32 p, t, 0; vote.sync.ballot.b32 a, p, 0xffffffff; @!p not.b32 a, a;\n"
+      " and.b32 t, %1, 64;  setp.ne.u32 p, t, 0; vote.sync.ballot.b32 b, p, 0xffffffff; @!p not.b32 b, b;\n"
+      " lop3.b32 %0, %0, a, b, 0x80;\n"
+      " and.b32 t, %1, 128; setp.ne.u32 p, t, 0; vote.sync.ballot.b32 a, p, 0xffffffff; @!p not.b32 a, a;\n"
+      " and.b32 %0, %0, a;\n"
       "}\n"
       : "=r"(peers)
       : "r"(d));
@@ -298,14 +309,24 @@ __global__ void __launch_bounds__(SORT_THREADS, 4) onesweep_kernel(const uint32_
   __syncthreads();
 
   // ---- coalesced per-digit runs to global -------------------------------------------------------------------
-  uint32_t* dst = out + seg_base;
+  // the segment base goes through an opaque register pair: nvcc otherwise re-derives seg * seg_len (two wide
+  // multiplies) for every key; with it a key costs LDS, PRMT, LDS, IADD, IMAD.WIDE, STG
+  uint32_t* dst = opaque_ptr(out + seg_base);
+  if (full) {
 #pragma unroll
-  for (int j = 0; j < SORT_ITEMS; ++j) {
-    const int pos = j * SORT_THREADS + tid;
-    if (full || pos < nvalid) {
+    for (int j = 0; j < SORT_ITEMS; ++j) {
+      const int pos = j * SORT_THREADS + tid;
       const uint32_t k = s_keys[pos];
-      const uint32_t d = digit_of(k, shift, sel);
-      dst[(uint32_t)(s_gbase[d] + (uint32_t)pos)] = k;
+      dst[(uint32_t)(s_gbase[digit_of(k, shift, sel)] + (uint32_t)pos)] = k;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < SORT_ITEMS; ++j) {
+      const int pos = j * SORT_THREADS + tid;
+      if (pos < nvalid) {
+        const uint32_t k = s_keys[pos];
+        dst[(uint32_t)(s_gbase[digit_of(k, shift, sel)] + (uint32_t)pos)] = k;
+      }
     }
   }
 }
