@@ -116,11 +116,17 @@ def test_embedding_evaluator_batch_equals_per_image_reference():
         if r is None:
             assert np.isnan(vals[i]).all()
         else:
-            np.testing.assert_allclose(vals[i], r, atol=1e-6)
+            # the metric contract (1e-6; exact counting in practice) holds on IDENTICAL scores: the conf map the kernel wrote
+            np.testing.assert_allclose(vals[i], O.eval_ood_measure(res.conf[i].cpu().numpy(), gt[i].numpy(), (13,)), atol=1e-9)
+            # against the oracle's own fp32 conf map a last-ulp score difference can swap a positive with a neighbouring
+            # negative: one swap moves FPR by 1 / N_neg (6.6e-5 on this 96x160 image)
+            np.testing.assert_allclose(vals[i], r, atol=2e-4)
             ref_vals.append(r)
         a, b = O.intersection_and_union(res.label[i].cpu().numpy().astype(np.int64), gt[i].numpy(), 13)
         inter_sum, union_sum = inter_sum + a, union_sum + b
     s = summarize(res.confusion.cpu().numpy(), vals)
     assert s["n_images_scored"] == 3
-    np.testing.assert_allclose([s["mean_auroc"], s["mean_aupr"], s["mean_fpr"]], np.mean(ref_vals, axis=0), atol=1e-6)
+    np.testing.assert_allclose([s["mean_auroc"], s["mean_aupr"], s["mean_fpr"]], np.mean(ref_vals, axis=0), atol=2e-4)
+    ok = ~np.isnan(vals[:, 0])
+    np.testing.assert_allclose([s["mean_auroc"], s["mean_aupr"], s["mean_fpr"]], vals[ok, :3].mean(axis=0), atol=1e-12)
     np.testing.assert_allclose(s["iou"], inter_sum / (union_sum + 1e-10), rtol=1e-12)
