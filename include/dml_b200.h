@@ -275,14 +275,16 @@ DML_API int dml_ood_eval_segments(uint32_t* keys, const long long* seg_stats, in
  * AUROC / FPR95 next to the per-image mean of anomaly/eval_ood_traditional.py:569,641).  Call between
  * dml_ood_keygen(..., sort_workspace = seg_workspace) and dml_ood_eval_segments(..., hist_precomputed = 1) of a
  * batch: the batch's per-segment digit histograms (still raw counts at that point) are added to the histogram slot
- * of `pooled_workspace`, the workspace of ONE segment of `pooled_len` keys (dml_ood_workspace_bytes(1, pooled_len));
- * `reset` != 0 overwrites instead of adding (first batch of a pooled evaluation).  When every batch wrote its keys
- * into consecutive slices of one buffer (all with the same key_base / score_kind), that buffer -- in whatever order
- * the per-batch sorts left it -- is then evaluated with
- *   dml_ood_eval_segments(all_keys, summed_seg_stats, 1, pooled_len, level, pooled_workspace, bytes, 1, result). */
-DML_API int dml_ood_pool_histograms(const void* seg_workspace, size_t seg_workspace_bytes, int32_t n_seg, int64_t seg_len,
-                            void* pooled_workspace, size_t pooled_workspace_bytes, int64_t pooled_len, int32_t reset,
-                            dml_stream_t stream);
+ * of `pooled_workspace`, the workspace of ONE segment of `pooled_len` keys (dml_ood_workspace_bytes(1, pooled_len)),
+ * and the batch's seg_stats rows (n_pos, n_nan, n_out_of_window, 0) to the 4 int64 of `pooled_stats`;
+ * `reset` != 0 overwrites instead of adding (first batch of a pooled evaluation).  `pooled_workspace` may be NULL
+ * (counts only: the multi-GPU path re-partitions the keys across ranks) and so may `pooled_stats`.
+ * When every batch wrote its keys into consecutive slices of one buffer (all with the same key_base / score_kind),
+ * that buffer -- in whatever order the per-batch sorts left it -- is then evaluated with
+ *   dml_ood_eval_segments(all_keys, pooled_stats, 1, pooled_len, level, pooled_workspace, bytes, 1, result). */
+DML_API int dml_ood_pool_histograms(const void* seg_workspace, size_t seg_workspace_bytes, const long long* seg_stats,
+                            int32_t n_seg, int64_t seg_len, void* pooled_workspace, size_t pooled_workspace_bytes,
+                            int64_t pooled_len, long long* pooled_stats, int32_t reset, dml_stream_t stream);
 
 /* Second FPR@recall convention, used by the reference's softmax-baseline evaluator
  * (DeepLabV3Plus-Pytorch/test.py:241-244): fpr[tpr >= recall_level][0] on

@@ -98,8 +98,8 @@ SIGNATURES = {
     "dml_ood_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int64]),
     "dml_ood_eval_segments": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_double, C.c_void_p,
                                         C.c_size_t, C.c_int32, C.c_void_p, C.c_void_p]),
-    "dml_ood_pool_histograms": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int32, C.c_int64, C.c_void_p, C.c_size_t, C.c_int64,
-                                          C.c_int32, C.c_void_p]),
+    "dml_ood_pool_histograms": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_size_t,
+                                          C.c_int64, C.c_void_p, C.c_int32, C.c_void_p]),
     "dml_ood_roc_fpr": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_double, C.c_void_p, C.c_size_t,
                                   C.c_void_p, C.c_void_p]),
     "dml_ood_sort": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_size_t,

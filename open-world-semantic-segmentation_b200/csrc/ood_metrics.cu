@@ -68,22 +68,12 @@ struct HistArgs {
   uint32_t* ghist;   // [n_seg][MAX_PASSES][RADIX] inside the sort workspace (zeroed by the caller)
   int n_passes;
   int shifts[MAX_PASSES];
+  int top_atomic;    // count the (skewed) top digit place with shared atomics too instead of ballot groups
 };
 __device__ __forceinline__ unsigned lanemask_lt_() {
   unsigned m;
   asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
   return m;
-}
-// lanes of the warp holding the same 8-bit digit (8 ballots); every lane of the warp must call it
-__device__ __forceinline__ unsigned match8_ballot(uint32_t d) {
-  unsigned peers = 0xffffffffu;
-#pragma unroll
-  for (int b = 0; b < RADIX_BITS; ++b) {
-    const bool bit = (d >> b) & 1u;
-    const unsigned vote = __ballot_sync(0xffffffffu, bit);
-    peers &= bit ? vote : ~vote;
-  }
-  return peers;
 }
 // HIST: the digit histograms of all radix passes (the sort's up-front counting read) are accumulated here, while
 // the keys are still in registers: key-gen is HBM-bound and the histogram is shared-atomic-bound, so the two overlap
@@ -169,21 +159,30 @@ __global__ void __launch_bounds__(256) keygen_kernel(const float* __restrict__ v
     if constexpr (HIST) {
       const int w = threadIdx.x >> 5;
       const unsigned lt = lanemask_lt_();
+      const unsigned vm = ballot_all(live);   // the VEC keys of a thread share it
+      // the fused form always counts the full 32-bit key: MAX_PASSES digit places at shifts 0, 8, 16, 24
+      // (dml_ood_keygen checks the plan).  The lower places of float keys are close to uniform: plain shared atomics.
 #pragma unroll
       for (int j = 0; j < VEC; ++j) {
+        if (live) {
 #pragma unroll
-        for (int p = 0; p < MAX_PASSES; ++p) {
-          if (p < hz.n_passes) {
-            const uint32_t d = (key[j] >> hz.shifts[p]) & (RADIX - 1);
-            if (p < hz.n_passes - 1) {
-              if (live) atomicAdd(&s_h[w][p][d], 1u);
-            } else {
-              const unsigned vm = __ballot_sync(0xffffffffu, live);
-              const unsigned peers = match8_ballot(d) & vm;
-              if (live && (peers & lt) == 0u) s_h[w][p][d] += (uint32_t)__popc(peers);
-              __syncwarp();
-            }
-          }
+          for (int p = 0; p < MAX_PASSES - 1; ++p) atomicAdd(&s_h[w][p][(key[j] >> (p * RADIX_BITS)) & (RADIX - 1)], 1u);
+        }
+      }
+      // the top place is heavily skewed (a warp usually holds 1-3 distinct values): group equal digits with ballots,
+      // the group's lowest lane adds the group size with a plain read-modify-write.  Bare VOTEs (match8_full /
+      // ballot_all): all lanes get here, the trip count is block-uniform.
+      if (hz.top_atomic) {
+#pragma unroll
+        for (int j = 0; j < VEC; ++j)
+          if (live) atomicAdd(&s_h[w][MAX_PASSES - 1][key[j] >> ((MAX_PASSES - 1) * RADIX_BITS)], 1u);
+      } else {
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+          const uint32_t d = key[j] >> ((MAX_PASSES - 1) * RADIX_BITS);
+          const unsigned peers = match8_full(d) & vm;
+          if (live && (peers & lt) == 0u) s_h[w][MAX_PASSES - 1][d] += (uint32_t)__popc(peers);
+          __syncwarp();
         }
       }
     }
@@ -202,7 +201,7 @@ __global__ void __launch_bounds__(256) keygen_kernel(const float* __restrict__ v
   }
   if constexpr (HIST) {
     __syncthreads();
-    for (int i = threadIdx.x; i < hz.n_passes * RADIX; i += 256) {
+    for (int i = threadIdx.x; i < MAX_PASSES * RADIX; i += 256) {
       const int p = i >> RADIX_BITS, d = i & (RADIX - 1);
       uint32_t c = 0;
 #pragma unroll
@@ -911,9 +910,32 @@ int run_scan(const uint32_t* sorted, const MetricsPlan& m, unsigned char* ws, co
   return DML_OK;
 }
 
-// pooled[p][d] (+)= sum over segments of seg_hist[seg][p][d]; one thread per (pass, digit), coalesced over digits
+// blocks 0..MAX_PASSES-1: pooled[p][d] (+)= sum over segments of seg_hist[seg][p][d] (one thread per (pass, digit),
+// coalesced over digits); block MAX_PASSES: pooled_stats[c] (+)= sum over segments of seg_stats[seg][c]
 __global__ void __launch_bounds__(RADIX) pool_hist_kernel(const uint32_t* __restrict__ seg_hist, int n_seg,
-                                                          uint32_t* __restrict__ pooled, int reset) {
+                                                          uint32_t* __restrict__ pooled, int reset,
+                                                          const unsigned long long* __restrict__ seg_stats,
+                                                          unsigned long long* __restrict__ pooled_stats) {
+  if (blockIdx.x == MAX_PASSES) {
+    if (!seg_stats || !pooled_stats) return;
+    __shared__ unsigned long long s_s[4][RADIX];
+    unsigned long long a[4] = {0ull, 0ull, 0ull, 0ull};
+    for (int sg = threadIdx.x; sg < n_seg; sg += RADIX)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) a[c] += seg_stats[(size_t)sg * 4 + c];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) s_s[c][threadIdx.x] = a[c];
+    __syncthreads();
+    for (int o = RADIX / 2; o > 0; o >>= 1) {
+      if ((int)threadIdx.x < o)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) s_s[c][threadIdx.x] += s_s[c][threadIdx.x + o];
+      __syncthreads();
+    }
+    if (threadIdx.x < 4) pooled_stats[threadIdx.x] = (reset ? 0ull : pooled_stats[threadIdx.x]) + s_s[threadIdx.x][0];
+    return;
+  }
+  if (!seg_hist || !pooled) return;
   const int i = blockIdx.x * RADIX + threadIdx.x;   // p * RADIX + d
   uint32_t c = reset ? 0u : pooled[i];
   for (int s = 0; s < n_seg; ++s) c += seg_hist[(size_t)s * MAX_PASSES * RADIX + i];
@@ -981,7 +1003,10 @@ int dml_ood_keygen(const float* values, const float* minmax, int32_t minmax_slot
     if (sort_workspace_bytes < plan.off_end) return DML_ERR_WORKSPACE;
     hz.ghist = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(sort_workspace) + plan.off_hist);
     hz.n_passes = plan.n_passes;
+    if (plan.n_passes != MAX_PASSES) return DML_ERR_INVALID_ARG;   // the kernel hard-codes the 4 x 8-bit places
     for (int p = 0; p < MAX_PASSES; ++p) hz.shifts[p] = plan.shifts[p];
+    const char* ta = getenv("DML_KEYGEN_TOP_ATOMIC");   // A-B knob, read per call
+    hz.top_atomic = (ta && ta[0] == '1') ? 1 : 0;
     DML_CUDA_TRY(cudaMemsetAsync(hz.ghist, 0, plan.off_lookback - plan.off_hist, stream));
   }
 #define DML_KEYGEN_LAUNCH(GT, V, gtp, posp)                                                                          \
@@ -1027,22 +1052,29 @@ int dml_ood_eval_segments(uint32_t* keys, const long long* seg_stats, int32_t n_
   return run_scan(sorted, m, ws, info, recall_level, (const unsigned long long*)seg_stats, results, nullptr, stream);
 }
 
-int dml_ood_pool_histograms(const void* seg_workspace, size_t seg_workspace_bytes, int32_t n_seg, int64_t seg_len,
-                            void* pooled_workspace, size_t pooled_workspace_bytes, int64_t pooled_len, int32_t reset,
-                            dml_stream_t stream_) {
+int dml_ood_pool_histograms(const void* seg_workspace, size_t seg_workspace_bytes, const long long* seg_stats, int32_t n_seg,
+                            int64_t seg_len, void* pooled_workspace, size_t pooled_workspace_bytes, int64_t pooled_len,
+                            long long* pooled_stats, int32_t reset, dml_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  if (!seg_workspace || !pooled_workspace || n_seg < 0 || n_seg > 65535 || seg_len < 0 || pooled_len < 0) return DML_ERR_INVALID_ARG;
+  if (n_seg < 0 || n_seg > 65535 || seg_len < 0 || pooled_len < 0) return DML_ERR_INVALID_ARG;
   if (seg_len >= (1ll << 32) || pooled_len >= (1ll << 32)) return DML_ERR_INVALID_ARG;
-  const SortPlan seg_plan = make_sort_plan(n_seg > 0 ? n_seg : 1, seg_len, 0, 32);
-  const SortPlan pool_plan = make_sort_plan(1, pooled_len, 0, 32);
-  if (seg_workspace_bytes < seg_plan.off_end || pooled_workspace_bytes < pool_plan.off_end) return DML_ERR_WORKSPACE;
-  const uint32_t* sh = reinterpret_cast<const uint32_t*>(reinterpret_cast<const unsigned char*>(seg_workspace) + seg_plan.off_hist);
-  uint32_t* ph = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(pooled_workspace) + pool_plan.off_hist);
+  if ((pooled_workspace && !seg_workspace) || (pooled_stats && !seg_stats)) return DML_ERR_INVALID_ARG;
+  const uint32_t* sh = nullptr;
+  uint32_t* ph = nullptr;
+  if (pooled_workspace) {
+    const SortPlan seg_plan = make_sort_plan(n_seg > 0 ? n_seg : 1, seg_len, 0, 32);
+    const SortPlan pool_plan = make_sort_plan(1, pooled_len, 0, 32);
+    if (seg_workspace_bytes < seg_plan.off_end || pooled_workspace_bytes < pool_plan.off_end) return DML_ERR_WORKSPACE;
+    sh = reinterpret_cast<const uint32_t*>(reinterpret_cast<const unsigned char*>(seg_workspace) + seg_plan.off_hist);
+    ph = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(pooled_workspace) + pool_plan.off_hist);
+  }
   if (n_seg == 0 || seg_len == 0) {
-    if (reset) DML_CUDA_TRY(cudaMemsetAsync(ph, 0, (size_t)MAX_PASSES * RADIX * sizeof(uint32_t), stream));
+    if (reset && ph) DML_CUDA_TRY(cudaMemsetAsync(ph, 0, (size_t)MAX_PASSES * RADIX * sizeof(uint32_t), stream));
+    if (reset && pooled_stats) DML_CUDA_TRY(cudaMemsetAsync(pooled_stats, 0, 4 * sizeof(long long), stream));
     return DML_OK;
   }
-  pool_hist_kernel<<<MAX_PASSES, RADIX, 0, stream>>>(sh, n_seg, ph, reset);
+  pool_hist_kernel<<<MAX_PASSES + 1, RADIX, 0, stream>>>(sh, n_seg, ph, reset, (const unsigned long long*)seg_stats,
+                                                         (unsigned long long*)pooled_stats);
   DML_LAUNCH_CHECK();
   return DML_OK;
 }

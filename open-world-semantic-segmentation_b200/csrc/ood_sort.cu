@@ -49,32 +49,6 @@ __device__ __forceinline__ unsigned match_digit8(uint32_t d, bool valid) {
   return valid ? peers : 0u;
 }
 
-// Peer mask for one 8-bit digit: per bit a predicate test, VOTE and a predicated NOT; the eight terms are folded with
-// three-input LOP3s (a & b & c), four instead of seven ANDs.  nvcc's own code for the C++ form above spends 6 per bit.
-__device__ __forceinline__ unsigned match8_full(uint32_t d) {
-  unsigned peers;
-  asm volatile(
-      "{\n"
-      " .reg .pred p;\n"
-      " .reg .b32 a, b, t;\n"
-      " and.b32 t, %1, 1;   setp.ne.u32 p, t, 0; vote.sync.ballot.b32 %0, p, 0xffffffff; @!p not.b32 %0, %0;\n"
-      " and.b32 t, %1, 2;   setp.ne.u32 p, t, 0; vote.sync.ballot.b32 a, p, 0xffffffff; @!p not.b32 a, a;\n"
-      " and.b32 t, %1, 4;   setp.ne.u32 p, t, 0; vote.sync.ballot.b32 b, p, 0xffffffff; @!p not.b32 b, b;\n"
-      " lop3.b32 %0, %0, a, b, 0x80;\n"
-      " and.b32 t, %1, 8;   setp.ne.u32 p, t, 0; vote.sync.ballot.b32 a, p, 0xffffffff; @!p not.b32 a, a;\n"
-      " and.b32 t, %1, 16;  setp.ne.u32 p, t, 0; vote.sync.ballot.b32 b, p, 0xffffffff; @!p not.b32 b, b;\n"
-      " lop3.b32 %0, %0, a, b, 0x80;\n"
-      " and.b32 t, %1, 32;  setp.ne.u32 p, t, 0; vote.sync.ballot.b32 a, p, 0xffffffff; @!p not.b32 a, a;\n"
-      " and.b32 t, %1, 64;  setp.ne.u32 p, t, 0; vote.sync.ballot.b32 b, p, 0xffffffff; @!p not.b32 b, b;\n"
-      " lop3.b32 %0, %0, a, b, 0x80;\n"
-      " and.b32 t, %1, 128; setp.ne.u32 p, t, 0; vote.sync.ballot.b32 a, p, 0xffffffff; @!p not.b32 a, a;\n"
-      " and.b32 %0, %0, a;\n"
-      "}\n"
-      : "=r"(peers)
-      : "r"(d));
-  return peers;
-}
-
 // ---- digit histograms of every pass in one read of the keys --------------------------------
 // Warp-private shared histograms updated by the match-group leader with plain LDS/STS (no atomics).
 constexpr int HIST_TILES_PER_BLOCK = 16;

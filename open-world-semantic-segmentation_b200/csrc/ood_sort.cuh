@@ -35,6 +35,49 @@ struct SortPlan {
   size_t off_alt, off_hist, off_lookback, off_ticket, off_end;
 };
 
+// Peer mask for one 8-bit digit: per bit a predicate test, VOTE and a predicated NOT; the eight terms are folded with
+// three-input LOP3s (a & b & c), four instead of seven ANDs.  nvcc's own code for a C++ loop over __ballot_sync spends 6
+// per bit, and ~30 where it cannot prove the warp converged (WARPSYNC / ENDCOLLECTIVE around every vote).
+__device__ __forceinline__ unsigned match8_full(uint32_t d) {
+  unsigned peers;
+  asm volatile(
+      "{\n"
+      " .reg .pred p;\n"
+      " .reg .b32 a, b, t;\n"
+      " and.b32 t, %1, 1;   setp.ne.u32 p, t, 0; vote.sync.ballot.b32 %0, p, 0xffffffff; @!p not.b32 %0, %0;\n"
+      " and.b32 t, %1, 2;   setp.ne.u32 p, t, 0; vote.sync.ballot.b32 a, p, 0xffffffff; @!p not.b32 a, a;\n"
+      " and.b32 t, %1, 4;   setp.ne.u32 p, t, 0; vote.sync.ballot.b32 b, p, 0xffffffff; @!p not.b32 b, b;\n"
+      " lop3.b32 %0, %0, a, b, 0x80;\n"
+      " and.b32 t, %1, 8;   setp.ne.u32 p, t, 0; vote.sync.ballot.b32 a, p, 0xffffffff; @!p not.b32 a, a;\n"
+      " and.b32 t, %1, 16;  setp.ne.u32 p, t, 0; vote.sync.ballot.b32 b, p, 0xffffffff; @!p not.b32 b, b;\n"
+      " lop3.b32 %0, %0, a, b, 0x80;\n"
+      " and.b32 t, %1, 32;  setp.ne.u32 p, t, 0; vote.sync.ballot.b32 a, p, 0xffffffff; @!p not.b32 a, a;\n"
+      " and.b32 t, %1, 64;  setp.ne.u32 p, t, 0; vote.sync.ballot.b32 b, p, 0xffffffff; @!p not.b32 b, b;\n"
+      " lop3.b32 %0, %0, a, b, 0x80;\n"
+      " and.b32 t, %1, 128; setp.ne.u32 p, t, 0; vote.sync.ballot.b32 a, p, 0xffffffff; @!p not.b32 a, a;\n"
+      " and.b32 %0, %0, a;\n"
+      "}\n"
+      : "=r"(peers)
+      : "r"(d));
+  return peers;
+}
+
+// ballot of a per-lane flag as a bare VOTE: inside loops whose convergence nvcc cannot prove, the C++ __ballot_sync is
+// wrapped in a WARPSYNC / ENDCOLLECTIVE protocol that costs ~10 instructions per call.  Every lane of the warp must
+// reach the call (the callers iterate to warp-uniform bounds).
+__device__ __forceinline__ unsigned ballot_all(bool flag) {
+  unsigned r;
+  asm volatile(
+      "{\n"
+      " .reg .pred q;\n"
+      " setp.ne.u32 q, %1, 0;\n"
+      " vote.sync.ballot.b32 %0, q, 0xffffffff;\n"
+      "}\n"
+      : "=r"(r)
+      : "r"((unsigned)flag));
+  return r;
+}
+
 SortPlan make_sort_plan(int n_seg, long long seg_len, int begin_bit, int end_bit);
 // sort; returns pointer to the buffer that holds the result (keys or the alt buffer in workspace)
 // `hist_done`: the digit histograms in the workspace were already accumulated by the key-generation kernel

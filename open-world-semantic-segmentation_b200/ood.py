@@ -178,11 +178,9 @@ def eval_segments(values: torch.Tensor, n_seg: int, seg_len: int, *, gt: Optiona
               "dml_ood_keygen")
         if pool is not None and n > 0:
             # between key-gen and the sort the workspace holds the raw per-segment digit counts
-            if pool.scratch is not None:
-                check(lib().dml_ood_pool_histograms(ptr(scratch), scratch.numel(), n_seg, seg_len, ptr(pool.scratch),
-                                                    pool.scratch.numel(), pool.capacity, 1 if pool.n == n else 0, s),
-                      "dml_ood_pool_histograms")
-            pool.stats += stats.sum(dim=0, keepdim=True)
+            check(lib().dml_ood_pool_histograms(ptr(scratch), scratch.numel(), ptr(stats), n_seg, seg_len, ptr(pool.scratch),
+                                                pool.scratch.numel() if pool.scratch is not None else 0, pool.capacity,
+                                                ptr(pool.stats), 1 if pool.n == n else 0, s), "dml_ood_pool_histograms")
         check(lib().dml_ood_eval_segments(ptr(keys), ptr(stats), n_seg, seg_len, recall_level, ptr(scratch),
                                           scratch.numel(), 1 if fused_hist else 0, ptr(results), s), "dml_ood_eval_segments")
     return results, stats
