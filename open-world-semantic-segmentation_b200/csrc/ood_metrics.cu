@@ -169,8 +169,9 @@ __global__ void __launch_bounds__(256) keygen_kernel(const float* __restrict__ v
           for (int p = 0; p < MAX_PASSES - 1; ++p) atomicAdd(&s_h[w][p][(key[j] >> (p * RADIX_BITS)) & (RADIX - 1)], 1u);
         }
       }
-      // the top place is heavily skewed (a warp usually holds 1-3 distinct values): group equal digits with ballots,
-      // the group's lowest lane adds the group size with a plain read-modify-write.  Bare VOTEs (match8_full /
+      // the top place is heavily skewed (a warp usually holds 1-3 distinct values).  Default: shared atomics as well
+      // (ATOMS.POPC.INC counts the same-address lanes in one operation).  Alternative: group equal digits with ballots,
+      // the group's lowest lane adds the group size with a plain read-modify-write -- bare VOTEs (match8_full /
       // ballot_all): all lanes get here, the trip count is block-uniform.
       if (hz.top_atomic) {
 #pragma unroll
@@ -1005,8 +1006,11 @@ int dml_ood_keygen(const float* values, const float* minmax, int32_t minmax_slot
     hz.n_passes = plan.n_passes;
     if (plan.n_passes != MAX_PASSES) return DML_ERR_INVALID_ARG;   // the kernel hard-codes the 4 x 8-bit places
     for (int p = 0; p < MAX_PASSES; ++p) hz.shifts[p] = plan.shifts[p];
-    const char* ta = getenv("DML_KEYGEN_TOP_ATOMIC");   // A-B knob, read per call
-    hz.top_atomic = (ta && ta[0] == '1') ? 1 : 0;
+    // measured on B200 (profiles/r1e_*): ATOMS.POPC.INC merges same-address lanes in hardware, so even the heavily
+    // skewed top place is cheaper with shared atomics (key-gen 266 us / 46 M keys) than with ballot groups (306 us);
+    // DML_KEYGEN_TOP_ATOMIC=0 selects the ballot form (A-B knob, read per call)
+    const char* ta = getenv("DML_KEYGEN_TOP_ATOMIC");
+    hz.top_atomic = (ta && ta[0] == '0') ? 0 : 1;
     DML_CUDA_TRY(cudaMemsetAsync(hz.ghist, 0, plan.off_lookback - plan.off_hist, stream));
   }
 #define DML_KEYGEN_LAUNCH(GT, V, gtp, posp)                                                                          \

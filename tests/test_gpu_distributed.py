@@ -40,14 +40,25 @@ def _worker(rank, world, port, mode, q):
     try:
         from dml_b200 import distributed as D
         conf, gt = _shard(rank)
-        a, p, f, info = D.pooled_measures(torch.from_numpy(conf).cuda(), torch.from_numpy(gt).cuda(), (13,), mode=mode)
+        if mode.endswith("+pool"):
+            # the bench's flow: the per-image evaluation (10 "images" of 30 000 pairs, two batches) leaves its keys and
+            # counts in an ood.KeyPool; the pooled exchange starts from those keys instead of generating them again
+            from dml_b200 import ood
+            pool = ood.KeyPool(conf.size, "cuda", histograms=False)
+            c, g = torch.from_numpy(conf).cuda().view(10, -1), torch.from_numpy(gt).cuda().view(10, -1)
+            for s0, s1 in ((0, 6), (6, 10)):
+                ood.eval_segments(c[s0:s1], s1 - s0, c.shape[1], gt=g[s0:s1], out_labels=(13,), pool=pool)
+            a, p, f, info = D.pooled_measures(None, None, (13,), mode=mode.split("+")[0],
+                                              keys_and_stats=(pool.keys, pool.stats[0]))
+        else:
+            a, p, f, info = D.pooled_measures(torch.from_numpy(conf).cuda(), torch.from_numpy(gt).cuda(), (13,), mode=mode)
         q.put((rank, a, p, f, info))
     finally:
         dist.destroy_process_group()
 
 
 @pytest.mark.parametrize("world", [1, 2])
-@pytest.mark.parametrize("mode", ["partition", "alltoall", "allgather"])
+@pytest.mark.parametrize("mode", ["partition", "alltoall", "allgather", "partition+pool", "allgather+pool"])
 def test_pooled_measures_nccl(world, mode):
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
