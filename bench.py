@@ -381,9 +381,9 @@ def run_ours(args):
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
     if world > 1:
-        # keep stdout to the ONE JSON line: NCCL prints its version banner to stdout at NCCL_DEBUG=VERSION
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # keep stdout to the ONE JSON line: NCCL writes its version banner (NCCL_DEBUG >= VERSION, which this image's
+        # launcher environment sets) and its warnings to stdout unless told otherwise -- send them to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         # the one large collective of the step is the all-to-all of the key ranges (send/recv pairs): give the p2p
         # path every channel (measured with tools/bench_a2a.py on 2 x B200: 431 -> 632 GB/s per direction)
         for k, v in (("NCCL_MIN_P2P_NCHANNELS", "64"), ("NCCL_MAX_P2P_NCHANNELS", "64"), ("NCCL_MIN_NCHANNELS", "64")):

@@ -35,7 +35,8 @@ struct SortPlan {
   size_t off_alt, off_hist, off_lookback, off_ticket, off_end;
 };
 
-// Peer mask for one 8-bit digit: per bit a predicate test, VOTE and a predicated NOT; the eight terms are folded with
+// Peer mask of the lanes holding the same 8-bit digit from 8 warp ballots (full-rate VOTE + LOP3; MATCH.ANY is far slower
+// on sm_100): per bit a predicate test, VOTE and a predicated NOT; the eight terms are folded with
 // three-input LOP3s (a & b & c), four instead of seven ANDs.  nvcc's own code for a C++ loop over __ballot_sync spends 6
 // per bit, and ~30 where it cannot prove the warp converged (WARPSYNC / ENDCOLLECTIVE around every vote).
 __device__ __forceinline__ unsigned match8_full(uint32_t d) {
