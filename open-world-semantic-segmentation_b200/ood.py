@@ -164,9 +164,10 @@ def eval_segments(values: torch.Tensor, n_seg: int, seg_len: int, *, gt: Optiona
             raise ValueError("gt must be uint8 or int64")
     else:
         raise ValueError("need gt or positive")
-    # batched segments: the sort's digit histograms are accumulated by the key-generation kernel (measured on B200:
-    # -1 ms per 1.38 G pairs for 50-image batches, +1.4 ms for one long segment, hence the n_seg rule;
-    # DML_FUSED_HIST=0 / 1 forces the separate / fused form)
+    # batched segments (and every pooled evaluation): the sort's digit histograms are accumulated by the key-generation
+    # kernel while the keys are in registers (B200: 264 us per 46 M keys against 231 us key-gen + 227 us separate counting
+    # read); one long segment keeps the separate hist_kernel (few, long look-back chains: the fused form measured
+    # slower there).  DML_FUSED_HIST=0 / 1 forces the separate / fused form.
     fh = os.environ.get("DML_FUSED_HIST", "")
     fused_hist = n > 0 and (fh == "1" or (fh != "0" and n_seg >= 4) or pool is not None)
     with torch.cuda.device(dev):
