@@ -237,7 +237,7 @@ def run_reference(args):
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "port", "sample": sample, **detail},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit_json_line(line)
 
 
 def workload_name(args):
@@ -381,9 +381,6 @@ def run_ours(args):
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
     if world > 1:
-        # keep stdout to the ONE JSON line: NCCL writes its version banner (NCCL_DEBUG >= VERSION, which this image's
-        # launcher environment sets) and its warnings to stdout unless told otherwise -- send them to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         # the one large collective of the step is the all-to-all of the key ranges (send/recv pairs): give the p2p
         # path every channel (measured with tools/bench_a2a.py on 2 x B200: 431 -> 632 GB/s per direction)
         for k, v in (("NCCL_MIN_P2P_NCHANNELS", "64"), ("NCCL_MAX_P2P_NCHANNELS", "64"), ("NCCL_MIN_NCHANNELS", "64")):
@@ -546,7 +543,7 @@ def run_ours(args):
                          "ms_per_step": e2e["ms_per_step"], "steps": e2e["steps"], "note": e2e["note"],
                          "cpus_bound_to_gpu_numa_node": numa_cpus} if e2e else None),
                 "gpu_launches": int(launches), "clocks": clocks, "results": summary}
-        print(json.dumps(line))
+        emit_json_line(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -621,8 +618,28 @@ def run_e2e(args, pipe, x_all, gt_all, device, world, barrier):
                     f"on a copy stream; results (per-image metrics, confusion, pooled) copied D2H"}
 
 
+_JSON_OUT = None
+
+
+def claim_stdout():
+    """stdout carries exactly ONE JSON line.  Native libraries write there too (NCCL prints its version banner to fd 1
+    whenever the environment sets NCCL_DEBUG), so fd 1 is pointed at stderr for the whole run and the JSON line goes to
+    a private duplicate of the original stdout."""
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit_json_line(line):
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
     args = parse_args()
+    claim_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
