@@ -29,23 +29,7 @@ constexpr int SCAN_WARPS = SCAN_THREADS / 32;
 // ---------------------------------------------------------------------------------------------
 // key generation
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t pack_key(float v, int kind, bool pos, uint32_t key_base, unsigned& n_nan,
-                                             unsigned& n_oow) {
-  float f = kind == 0 ? v : -v;
-  if (f != f) {
-    ++n_nan;
-    return 0xfffffffeu | (pos ? 1u : 0u);
-  }
-  if (f == 0.f) f = 0.f;  // -0 and +0 are one threshold
-  const uint32_t u = __float_as_uint(f);
-  const uint32_t srt = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-  uint32_t rel = srt - key_base;
-  if (srt < key_base || rel >= 0x80000000u) {
-    ++n_oow;
-    rel = srt < key_base ? 0u : 0x7fffffffu;
-  }
-  return (rel << 1) | (pos ? 1u : 0u);
-}
+// pack_key(): ood_scan_thread.cuh (host / device, exercised on the CPU by tests/test_scan_emulation.py)
 
 template <typename GT>
 __device__ __forceinline__ bool is_positive(const GT* gt, const uint8_t* pos_u8, uint64_t mask, size_t i) {

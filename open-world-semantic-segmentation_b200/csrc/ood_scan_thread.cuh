@@ -15,6 +15,7 @@
 #pragma once
 #include <math.h>
 #include <stdint.h>
+#include <string.h>
 
 #if defined(__CUDACC__)
 #define DML_HD __host__ __device__ __forceinline__
@@ -45,6 +46,40 @@ struct TilePartial {
   long long n_groups;
   long long reserved;
 };
+
+// ---- ranking keys ------------------------------------------------------------------------------------------
+DML_HD uint32_t float_bits(float f) {
+#if defined(__CUDA_ARCH__)
+  return __float_as_uint(f);
+#else
+  uint32_t u;
+  memcpy(&u, &f, sizeof(u));
+  return u;
+#endif
+}
+// Order-preserving packed key of one (value, label) pair: kind 0 ranks a conf map (score = -conf, positives expected at
+// LOW conf: anomaly/eval_ood_traditional.py:139-141), kind 1 a plain score (higher = more positive).  Ascending key order
+// == descending score order; -0 and +0 are one threshold; the key is taken relative to `key_base` and must fit 31 bits
+// (violations are counted and clamped, NaNs counted and ranked last); bit 0 carries the positive flag, so inside a group of
+// equal score the negatives sort first.
+DML_HD uint32_t pack_key(float v, int kind, bool pos, uint32_t key_base, unsigned& n_nan,
+                                             unsigned& n_oow) {
+  float f = kind == 0 ? v : -v;
+  if (f != f) {
+    ++n_nan;
+    return 0xfffffffeu | (pos ? 1u : 0u);
+  }
+  if (f == 0.f) f = 0.f;  // -0 and +0 are one threshold
+  const uint32_t u = float_bits(f);
+  const uint32_t srt = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+  uint32_t rel = srt - key_base;
+  if (srt < key_base || rel >= 0x80000000u) {
+    ++n_oow;
+    rel = srt < key_base ? 0u : 0x7fffffffu;
+  }
+  return (rel << 1) | (pos ? 1u : 0u);
+}
+
 
 // ---- operators shared by the kernels and the host emulation ------------------------------------------------
 DML_HD Agg agg_combine(const Agg& a, const Agg& b) {

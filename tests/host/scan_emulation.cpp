@@ -176,3 +176,14 @@ extern "C" long long scan_emulate(const uint32_t* keys, long long n, long long p
   }
   return mismatches;
 }
+
+// dml_ood_keygen's packing (without the fused normalisation) for n (value, positive) pairs; counts[0] = NaNs,
+// counts[1] = keys outside the 31-bit window starting at key_base.
+extern "C" void pack_keys(const float* values, const uint8_t* positive, long long n, int kind, uint32_t key_base,
+                          uint32_t* keys, long long* counts) {
+  unsigned n_nan = 0, n_oow = 0;
+  for (long long i = 0; i < n; ++i) keys[i] = pack_key(values[i], kind, positive[i] != 0, key_base, n_nan, n_oow);
+  counts[0] = n_nan;
+  counts[1] = n_oow;
+}
+

@@ -24,7 +24,19 @@ def emu(tmp_path_factory):
     lib.scan_emulate.restype = ctypes.c_longlong
     lib.scan_emulate.argtypes = [ctypes.c_void_p, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_longlong,
                                  ctypes.c_longlong, ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p]
+    lib.pack_keys.restype = None
+    lib.pack_keys.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int, ctypes.c_uint32,
+                              ctypes.c_void_p, ctypes.c_void_p]
     return lib
+
+
+def _pack(emu, values, pos, kind, key_base):
+    values = np.ascontiguousarray(values, dtype=np.float32)
+    pos = np.ascontiguousarray(pos, dtype=np.uint8)
+    keys = np.zeros(values.size, np.uint32)
+    counts = np.zeros(2, np.int64)
+    emu.pack_keys(values.ctypes.data, pos.ctypes.data, values.size, kind, key_base, keys.ctypes.data, counts.ctypes.data)
+    return keys, counts
 
 
 def _keys(conf, pos):
@@ -121,3 +133,47 @@ def test_scan_emulation_ranges_combine_like_one_segment(emu, kind):
     assert (au, fp) == (whole[0], whole[2])
     assert ap == pytest.approx(whole[1], abs=1e-14)
     assert groups == np.unique(keys >> 1).size
+
+
+def test_pack_key_is_order_preserving_and_matches_the_numpy_double(emu):
+    """the kernels' pack_key (csrc/ood_scan_thread.cuh) on the CPU: ascending key order == ascending conf (kind 0) /
+    descending score (kind 1), equal keys <=> equal values with -0 == +0, positives after negatives inside a value,
+    NaNs and window violations counted; and it is the packing tests/np_ops.py and `_keys` above assume."""
+    rng = np.random.default_rng(3)
+    v = np.concatenate([rng.random(5000), [0.0, -0.0, 1.0, 1.0, 2.0 ** -149, 2.0 ** -126, 0.5, 0.5]]).astype(np.float32)
+    pos = (rng.random(v.size) < 0.3)
+    keys, counts = _pack(emu, v, pos, 0, 0x80000000)
+    assert counts.tolist() == [0, 0]
+    np.testing.assert_array_equal(np.sort(keys), _keys(v, pos))
+    order = np.argsort(keys, kind="stable")
+    assert (np.diff(v[order].astype(np.float64)) >= 0).all()                 # ascending conf
+    same = (keys[order][1:] >> 1) == (keys[order][:-1] >> 1)
+    np.testing.assert_array_equal(same, v[order][1:] == v[order][:-1])      # groups == equal values (+-0 merged)
+    assert ((keys[order][1:] & 1)[same] >= (keys[order][:-1] & 1)[same]).all()   # negatives first inside a group
+    from tests.np_ops import NumpyOps
+    import torch
+    k2, st = NumpyOps().make_keys(torch.from_numpy(v), torch.from_numpy(np.where(pos, 13, 2)), (13,), 0x80000000)
+    np.testing.assert_array_equal(keys, k2.numpy().view(np.uint32))
+    assert int(st[0]) == int(pos.sum())
+    # plain scores of either sign (kind 1): descending score order, window chosen from the data like measures_from_scores
+    sc = (np.abs(rng.standard_normal(4000)) * 3 + 0.01).astype(np.float32)     # same sign: the keys span < 2^31 values
+    f = -sc
+    bits = np.where(f == 0, np.float32(0), f).view(np.uint32)
+    srt = np.where(bits & 0x80000000, ~bits, bits | np.uint32(0x80000000)).astype(np.uint32)
+    base = int(srt.min())
+    k1, c1 = _pack(emu, sc, np.zeros(sc.size, bool), 1, base)
+    assert c1.tolist() == [0, 0]
+    o1 = np.argsort(k1, kind="stable")
+    assert (np.diff(sc[o1].astype(np.float64)) <= 0).all()
+    # mixed-sign scores span more than 2^31 sortable values: counted, never silently wrapped (measures_from_scores then
+    # ranks the two signs as separate ranges)
+    wide = np.float32([-3.0, 2.0, 1e-3, -1e-3])
+    wb = np.where(-wide == 0, np.float32(0), -wide).view(np.uint32)
+    wsrt = np.where(wb & 0x80000000, ~wb, wb | np.uint32(0x80000000)).astype(np.uint32)
+    _, cw = _pack(emu, wide, [0, 0, 0, 0], 1, int(wsrt.min()))
+    assert cw[1] > 0
+    # NaN: counted, ranked last; out of window: counted and clamped to the window's ends
+    kn, cn = _pack(emu, np.float32([0.25, np.nan, -1.0, 0.5]), [0, 1, 0, 0], 0, 0x80000000)
+    assert cn.tolist() == [1, 1]
+    assert kn[1] == 0xFFFFFFFF and kn[2] == 0 and kn[0] < kn[3] < kn[1]
+
