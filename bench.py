@@ -241,7 +241,8 @@ def run_reference(args):
 
 
 def workload_name(args):
-    return (f"StreetHazards-test shape {args.images}x{args.height}x{args.width}, K=D={args.classes}: fused distance head "
+    shape = {(720, 1280): "StreetHazards-test shape", (1024, 2048): "Cityscapes shape"}.get((args.height, args.width), "shape")
+    return (f"{shape} {args.images}x{args.height}x{args.width}, K=D={args.classes}: fused distance head "
             f"+ dissum/EDS/MMSP/mix maps + confusion + exact per-image and pooled AUROC/AUPR/FPR95")
 
 
