@@ -1,6 +1,6 @@
 #!/bin/bash
 # Final 1-GPU visit of the round: parity tests, smoke, the bench line, the ncu launch list and a `--set full` capture.
-#   /usr/local/graft/bin/gpurun --timeout 600 -- 'bash tools/gpu_round3.sh r1f'
+#   /usr/local/graft/bin/gpurun --timeout 600 -- 'bash tools/gpu_round_final.sh r1f'
 set -u
 TAG=${1:-run}
 OUT=gpurun_out
