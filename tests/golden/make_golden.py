@@ -7,7 +7,7 @@ Run in the build container only (the reference does not travel to the GPU box):
     python tests/golden/make_golden.py
 
 Outputs (committed): metrics_kat.npz, head_anomaly.npz, head_deeplab.npz,
-evaluate_anomaly.npz, validate_deeplab.npz, loss.npz, segmetrics.npz.
+evaluate_anomaly.npz, evaluate_anomaly_modes.npz, validate_deeplab.npz, loss.npz, segmetrics.npz, roc_baseline.npz.
 Every array in them was produced by reference code, never by the oracle or the
 product.  Versions at generation time are stored in ``meta.json``.
 """
@@ -248,6 +248,66 @@ def gen_evaluate_anomaly():
             out[f"img{i}_union"] = ius[i][1]
         out["summary"] = np.array(summary)
     save("evaluate_anomaly.npz", **out)
+
+
+def gen_evaluate_anomaly_modes():
+    """The reference's evaluate() in its other score modes -- `--ood msp`, `--ood maxlogit` and `OOD.exclude_back`
+    (anomaly/eval_ood_traditional.py:212-214,276-278,288-290,302-305) -- one image per mode, same reduced model as
+    gen_evaluate_anomaly(): conf map handed to eval_ood_measure, its result, pred and the stride-8 embeddings."""
+    out = {}
+    modes = [("msp", False), ("maxlogit", False), ("dissum", True), ("msp", True), ("maxlogit", True)]
+    with reference("anomaly"):
+        import eval_ood_traditional as E
+        from models import models as M
+        from models import resnet
+        torch.manual_seed(31)
+        with contextlib.redirect_stdout(io.StringIO()):
+            enc = M.ResnetDilated(resnet.resnet18(pretrained=False), dilate_scale=8)
+            dec = M.PPMDeepsup_embedding(num_class=13, fc_dim=512, use_softmax=True)
+        dec.conv_last[4].weight.data.mul_(8.0)
+        dec.conv_last[4].bias.data.zero_()
+        module = M.SegmentationModule(enc, dec, nn.NLLLoss(ignore_index=-1))
+        lows, calls, preds = [], [], []
+        dec.conv_last.register_forward_hook(lambda m, i, o: lows.append(o.detach().clone().numpy()))
+        ref_measure, ref_acc = E.eval_ood_measure, E.accuracy
+
+        def spy_measure(conf, seg_label, cfg, mask=None):
+            res = ref_measure(conf, seg_label, cfg, mask=mask)
+            calls.append((np.array(conf), np.array(seg_label), res))
+            return res
+
+        def spy_acc(pred, label):
+            preds.append(np.array(pred))
+            return ref_acc(pred, label)
+
+        E.eval_ood_measure, E.accuracy = spy_measure, spy_acc
+        try:
+            H, W = 96, 160
+            sizes = [(40, 72), (56, 88), (64, 104), (72, 120), (80, 136)]
+            g = torch.Generator().manual_seed(32)
+            for mi, (mode, excl) in enumerate(modes):
+                cfg = CfgNode(DATASET=CfgNode(num_class=13, imgSizes=(1, 2, 3, 4, 5)),
+                              OOD=CfgNode(exclude_back=excl, ood=mode, out_labels=(13,)),
+                              VAL=CfgNode(visualize=False), DIR="/tmp")
+                seg = torch.randint(0, 13, (1, H, W), generator=g)
+                seg[0, 30:60, 40:110] = 13
+                seg[0, 0:3, :] = -1
+                loader = [[{"img_ori": np.zeros((H, W, 3), np.uint8),
+                            "img_data": [torch.randn(1, 3, h, w, generator=g) for h, w in sizes],
+                            "seg_label": seg, "info": f"m{mi}.jpg", "name": f"m{mi}"}]]
+                n0 = len(calls)
+                with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()):
+                    E.evaluate(module, loader, cfg, 0)
+                assert len(calls) == n0 + 1 and len(lows) == 5 * (mi + 1) and len(preds) == mi + 1
+                tag = f"{mode}_{'noback' if excl else 'all'}"
+                for sidx in range(5):
+                    out[f"{tag}_low{sidx}"] = lows[5 * mi + sidx]
+                conf, sg, res = calls[-1]
+                out[f"{tag}_conf"], out[f"{tag}_seg"], out[f"{tag}_res"] = conf, sg, np.float64(res)
+                out[f"{tag}_pred"] = preds[-1]
+        finally:
+            E.eval_ood_measure, E.accuracy = ref_measure, ref_acc
+    save("evaluate_anomaly_modes.npz", **out)
 
 
 def gen_validate_deeplab():
@@ -539,6 +599,11 @@ def gen_roc_baseline():
 def main():
     import sklearn
     import scipy
+    if len(sys.argv) > 1:                      # regenerate only the named fixtures: make_golden.py gen_evaluate_anomaly_modes ...
+        for name in sys.argv[1:]:
+            globals()[name]()
+        return
+    gen_evaluate_anomaly_modes()
     gen_metrics()
     gen_head_anomaly()
     gen_head_deeplab()

@@ -119,6 +119,23 @@ def test_evaluate_anomaly_end_to_end(golden):
     assert float(line.split("mean auroc =")[1].split()[0]) == pytest.approx(np.mean(aurocs), abs=1e-12)
 
 
+@pytest.mark.parametrize("mode,excl", [("msp", False), ("maxlogit", False), ("dissum", True), ("msp", True), ("maxlogit", True)])
+def test_evaluate_anomaly_other_score_modes(golden, mode, excl):
+    """`--ood msp` / `--ood maxlogit` / `OOD.exclude_back` of the reference's evaluate()
+    (anomaly/eval_ood_traditional.py:212-214,276-278,288-290,302-305), captured from the unmodified reference by
+    make_golden.py:gen_evaluate_anomaly_modes: pred, the conf map handed to eval_ood_measure and its result."""
+    g = golden("evaluate_anomaly_modes.npz")
+    tag = f"{mode}_{'noback' if excl else 'all'}"
+    lows = [torch.from_numpy(g[f"{tag}_low{s}"]) for s in range(5)]
+    seg = g[f"{tag}_seg"]
+    scores, _ = O.multiscale_scores(lows, O.make_centers(13), seg.shape)
+    np.testing.assert_array_equal(O.argmax_label(scores)[0], g[f"{tag}_pred"])       # exclude_back never changes pred
+    conf = {"msp": O.score_msp, "maxlogit": O.score_maxlogit}[mode](scores, excl) if mode != "dissum" \
+        else O.score_dissum(scores, 400.0, excl)
+    np.testing.assert_array_equal(conf, g[f"{tag}_conf"])
+    np.testing.assert_allclose(O.eval_ood_measure(conf, seg, (13,)), g[f"{tag}_res"], atol=1e-12)
+
+
 def test_validate_deeplab_npm(golden):
     g = golden("validate_deeplab.npz")
     proto = O.novel_prototype(g["prototypes"].tolist())
