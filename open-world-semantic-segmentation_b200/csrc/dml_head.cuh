@@ -10,6 +10,7 @@
 // DeepLabV3Plus-Pytorch/test_embedding.py:339-350,428-433,445 (see include/dml_b200.h).
 #pragma once
 #include "dml_common.cuh"
+#include "dml_bilinear.cuh"
 
 namespace dml {
 
@@ -136,8 +137,7 @@ __device__ __forceinline__ void ms_gather(const HeadArgs& a, int b, long long p0
 #pragma unroll 1
   for (int s = 0; s < a.ms_n; ++s) {
     const int hs = a.ms_h[s], ws = a.ms_w[s];
-    float h1r = __fmaf_rn(a.ms_rh[s], y + 0.5f, -0.5f);
-    h1r = h1r < 0.f ? 0.f : h1r;
+    const float h1r = bilinear_src(a.ms_rh[s], y);
     const int h1 = (int)h1r;
     const int dy = (h1 < hs - 1) ? ws : 0;
     const float h1l = h1r - h1, h0l = 1.0f - h1l;
@@ -145,8 +145,7 @@ __device__ __forceinline__ void ms_gather(const HeadArgs& a, int b, long long p0
     float w1l[VEC], w0l[VEC];
 #pragma unroll
     for (int v = 0; v < VEC; ++v) {
-      float w1r = __fmaf_rn(a.ms_rw[s], (xo + v) + 0.5f, -0.5f);
-      w1r = w1r < 0.f ? 0.f : w1r;
+      const float w1r = bilinear_src(a.ms_rw[s], xo + v);
       const int w1 = (int)w1r;
       dx[v] = (w1 < ws - 1) ? 1 : 0;
       w1l[v] = w1r - w1;
@@ -161,12 +160,8 @@ __device__ __forceinline__ void ms_gather(const HeadArgs& a, int b, long long p0
       for (int v = 0; v < VEC; ++v) {
         const float* r = q + o00[v];
         const float v00 = __ldg(r), v01 = __ldg(r + dx[v]), v10 = __ldg(r + dy), v11 = __ldg(r + dy + dx[v]);
-        const float t0 = __fmaf_rn(w0l[v], v00, __fmul_rn(w1l[v], v01));
-        const float t1 = __fmaf_rn(w0l[v], v10, __fmul_rn(w1l[v], v11));
-        const float val = __fmaf_rn(h0l, t0, __fmul_rn(h1l, t1));
-        float t = __fmul_rn(val, a.ms_inv);
-        if (!a.ms_recip) t = __fmaf_rn(__fmaf_rn(-a.ms_div, t, val), a.ms_inv, t);
-        x[k][v] = __fadd_rn(x[k][v], t);
+        const float val = bilinear_blend(w0l[v], w1l[v], h0l, h1l, v00, v01, v10, v11);
+        x[k][v] = bl_add(x[k][v], scale_share(val, a.ms_inv, a.ms_div, a.ms_recip != 0));
       }
       q += plane;
     }
@@ -174,11 +169,7 @@ __device__ __forceinline__ void ms_gather(const HeadArgs& a, int b, long long p0
 }
 
 // floor of torch's bilinear source index for output coordinate `dst` (same fp32 arithmetic as the taps)
-__device__ __forceinline__ int ms_src_floor(float scale, int dst) {
-  float r = __fmaf_rn(scale, dst + 0.5f, -0.5f);
-  r = r < 0.f ? 0.f : r;
-  return (int)r;
-}
+__device__ __forceinline__ int ms_src_floor(float scale, int dst) { return (int)bilinear_src(scale, dst); }
 
 // HEAD_MSS stage 1: copy the low-resolution footprint of the CTA's output tile (origin ty0, tx0) into shared
 // memory for every scale, laid out [row][col][ms_stride(D)] (class innermost).  Rows / columns past the map
