@@ -7,7 +7,7 @@ Run in the build container only (the reference does not travel to the GPU box):
     python tests/golden/make_golden.py
 
 Outputs (committed): metrics_kat.npz, head_anomaly.npz, head_deeplab.npz,
-evaluate_anomaly.npz, evaluate_anomaly_modes.npz, validate_deeplab.npz, loss.npz, segmetrics.npz, roc_baseline.npz.
+evaluate_anomaly.npz, evaluate_anomaly_modes.npz, config0_full_shape.npz, validate_deeplab.npz, loss.npz, segmetrics.npz, roc_baseline.npz.
 Every array in them was produced by reference code, never by the oracle or the
 product.  Versions at generation time are stored in ``meta.json``.
 """
@@ -310,6 +310,81 @@ def gen_evaluate_anomaly_modes():
     save("evaluate_anomaly_modes.npz", **out)
 
 
+def gen_config0_full_shape():
+    """BASELINE.json configs[0] at its real shape: the reference's evaluate() (`--ood dissum`) with a random-init
+    PSPNet-ResNet50dilated embedding model on 4 synthetic 720x1280 StreetHazards-shape images (5 scales), on the CPU.
+    Kept small: the stride-8 embeddings, pred and a subsampled conf map of image 0 only; results of all 4 images."""
+    out = {}
+    with reference("anomaly"):
+        import eval_ood_traditional as E
+        from models import models as M
+        from models import resnet
+        torch.manual_seed(0)
+        with contextlib.redirect_stdout(io.StringIO()):
+            enc = M.ResnetDilated(resnet.resnet50(pretrained=False), dilate_scale=8)
+            dec = M.PPMDeepsup_embedding(num_class=13, fc_dim=2048, use_softmax=True)
+        dec.conv_last[4].weight.data.mul_(0.3)       # random init gives |x|^2 ~ 196 (sum d ~ 2800 >= the 400 clamp everywhere -> 0/0);
+        # 0.3 puts the median sum d near 350 with a few % of the pixels on the clamp plateau (SURVEY.md section 8c)
+        dec.conv_last[4].bias.data.zero_()
+        module = M.SegmentationModule(enc, dec, nn.NLLLoss(ignore_index=-1))
+        lows, calls, preds, accs, ius = [], [], [], [], []
+        dec.conv_last.register_forward_hook(lambda m, i, o: lows.append(o.detach().clone().numpy()))
+        ref_measure, ref_acc, ref_iu = E.eval_ood_measure, E.accuracy, E.intersectionAndUnion
+
+        def spy_measure(conf, seg_label, cfg, mask=None):
+            res = ref_measure(conf, seg_label, cfg, mask=mask)
+            calls.append((np.array(conf), np.array(seg_label), res))
+            return res
+
+        def spy_acc(pred, label):
+            preds.append(np.array(pred))
+            r = ref_acc(pred, label)
+            accs.append(r)
+            return r
+
+        def spy_iu(pred, label, n):
+            r = ref_iu(pred, label, n)
+            ius.append(r)
+            return r
+
+        E.eval_ood_measure, E.accuracy, E.intersectionAndUnion = spy_measure, spy_acc, spy_iu
+        try:
+            H, W = 720, 1280
+            sizes = [(304, 536), (376, 672), (456, 800), (528, 936), (568, 1000)]      # anomaly/dataset.py:281-289 on 720x1280
+            cfg = CfgNode(DATASET=CfgNode(num_class=13, imgSizes=(1, 2, 3, 4, 5)),
+                          OOD=CfgNode(exclude_back=False, ood="dissum", out_labels=(13,)),
+                          VAL=CfgNode(visualize=False), DIR="/tmp")
+            g = torch.Generator().manual_seed(1)
+            loader = []
+            for i in range(4):
+                seg = torch.randint(0, 13, (1, H, W), generator=g)
+                seg[0, 100 + 50 * i:200 + 50 * i, 300:500] = 13
+                loader.append([{"img_ori": np.zeros((H, W, 3), np.uint8),
+                                "img_data": [torch.randn(1, 3, h, w, generator=g) for h, w in sizes],
+                                "seg_label": seg, "info": f"c0_{i}.jpg", "name": f"c0_{i}"}])
+            buf = io.StringIO()
+            with contextlib.redirect_stdout(buf), contextlib.redirect_stderr(io.StringIO()):
+                E.evaluate(module, loader, cfg, 0)
+        finally:
+            E.eval_ood_measure, E.accuracy, E.intersectionAndUnion = ref_measure, ref_acc, ref_iu
+        assert len(lows) == 20 and len(calls) == 4 and len(preds) == 4
+        for s_ in range(5):
+            out[f"img0_low{s_}"] = lows[s_]
+        out["img0_pred"] = preds[0].astype(np.uint8)
+        out["img0_conf_sub8"] = calls[0][0][::8, ::8].copy()
+        out["img0_seg"] = calls[0][1].astype(np.int16)
+        for i in range(4):
+            conf, seg, res = calls[i]
+            out[f"img{i}_res"] = np.float64(res)
+            out[f"img{i}_conf_sum"] = np.float64(conf.astype(np.float64).sum())
+            out[f"img{i}_conf_minmax_raw"] = np.float32([conf.min(), conf.max()])
+            out[f"img{i}_pred_hist"] = np.bincount(preds[i].reshape(-1).astype(np.int64), minlength=13)
+            out[f"img{i}_acc"] = np.float64([accs[i][0], accs[i][1]])
+            out[f"img{i}_inter"], out[f"img{i}_union"] = ius[i][0], ius[i][1]
+        out["summary"] = np.array([ln for ln in buf.getvalue().splitlines() if "mean auroc" in ln or "Mean IoU" in ln])
+    save("config0_full_shape.npz", **out)
+
+
 def gen_validate_deeplab():
     """Run the reference's test_embedding.validate() on a synthetic loader (batch 1) with a tiny
     backbone and capture preds / confusion matrix."""
@@ -604,6 +679,7 @@ def main():
             globals()[name]()
         return
     gen_evaluate_anomaly_modes()
+    gen_config0_full_shape()
     gen_metrics()
     gen_head_anomaly()
     gen_head_deeplab()

@@ -85,6 +85,19 @@ def test_multiscale_emulation_matches_the_reference_golden(emu, golden):
         np.testing.assert_array_equal(got.argmax(axis=1)[0], g[f"img{i}_pred"])
 
 
+def test_multiscale_emulation_config0_full_shape(emu, golden):
+    """BASELINE.json configs[0] at its real shape (720x1280, the five StreetHazards scales): the kernel's scalar arithmetic
+    applied to the stride-8 embeddings the reference produced gives exactly the reference's pred and conf map."""
+    g = golden("config0_full_shape.npz")
+    c = O.make_centers(13)
+    zs = [O.distance_logits(torch.from_numpy(g[f"img0_low{s}"]), c) for s in range(5)]
+    got = _emulate(emu, zs, 720, 1280)
+    np.testing.assert_array_equal(got.argmax(axis=1)[0], g["img0_pred"])
+    conf = O.score_dissum(torch.from_numpy(got), 400.0)
+    np.testing.assert_array_equal(conf[::8, ::8], g["img0_conf_sub8"])
+    assert float(conf.astype(np.float64).sum()) == float(g["img0_conf_sum"])
+
+
 def test_small_outputs_agree_to_the_last_ulps(emu):
     """below its parallel grain size torch's CPU upsample runs a serial loop with a different FMA contraction (its result
     then differs from its own large-output path, which is the one the kernel arithmetic reproduces): closeness only."""

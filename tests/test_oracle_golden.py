@@ -136,6 +136,33 @@ def test_evaluate_anomaly_other_score_modes(golden, mode, excl):
     np.testing.assert_allclose(O.eval_ood_measure(conf, seg, (13,)), g[f"{tag}_res"], atol=1e-12)
 
 
+def test_config0_full_shape_streethazards(golden):
+    """BASELINE.json configs[0] at its real shape (720x1280, 5 scales, PSPNet-ResNet50dilated random init, run through the
+    unmodified reference on the CPU by make_golden.py:gen_config0_full_shape): the oracle replays image 0 from the captured
+    stride-8 embeddings -- pred exact, conf exact (subsampled map + float64 sum), per-image AUROC / AUPR / FPR95, acc / IoU."""
+    g = golden("config0_full_shape.npz")
+    lows = [torch.from_numpy(g[f"img0_low{s}"]) for s in range(5)]
+    seg = g["img0_seg"].astype(np.int64)
+    assert seg.shape == (720, 1280)
+    scores, _ = O.multiscale_scores(lows, O.make_centers(13), seg.shape)
+    pred = O.argmax_label(scores)[0]
+    np.testing.assert_array_equal(pred, g["img0_pred"])
+    np.testing.assert_array_equal(np.bincount(pred.reshape(-1), minlength=13), g["img0_pred_hist"])
+    conf = O.score_dissum(scores, 400.0)
+    np.testing.assert_array_equal(conf[::8, ::8], g["img0_conf_sub8"])
+    assert float(conf.astype(np.float64).sum()) == float(g["img0_conf_sum"])
+    assert (conf == 1.0).mean() > 0.001                                    # the 400-clamp plateau is populated (ties)
+    np.testing.assert_allclose(O.eval_ood_measure(conf, seg, (13,)), g["img0_res"], atol=1e-12)
+    acc, pix = O.accuracy(pred, seg)
+    np.testing.assert_allclose([acc, pix], g["img0_acc"], atol=1e-15)
+    inter, union = O.intersection_and_union(pred, seg, 13)
+    np.testing.assert_array_equal(inter, g["img0_inter"])
+    np.testing.assert_array_equal(union, g["img0_union"])
+    # the run's summary line is the mean over the 4 images of the per-image results (eval_ood_traditional.py:569,641)
+    line = [s for s in g["summary"].tolist() if "mean auroc" in s][0]
+    assert float(line.split("mean auroc =")[1].split()[0]) == pytest.approx(np.mean([g[f"img{i}_res"][0] for i in range(4)]), abs=1e-12)
+
+
 def test_validate_deeplab_npm(golden):
     g = golden("validate_deeplab.npz")
     proto = O.novel_prototype(g["prototypes"].tolist())
