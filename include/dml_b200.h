@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define DML_B200_ABI_VERSION 3
+#define DML_B200_ABI_VERSION 4
 
 #if defined(__GNUC__)
 #define DML_API __attribute__((visibility("default")))
@@ -114,6 +114,11 @@ typedef struct dml_head_params {
   const int64_t* gt_i64;      /* [B,H,W] */
   unsigned long long* confusion; /* [conf_rows, conf_cols] += count; gt outside [0,conf_rows) ignored */
   int32_t conf_rows, conf_cols;
+  int32_t reference_order;    /* != 0 (mu == NULL, D < 16, logits requested): parity mode -- every z_k is rounded exactly
+                                 like the reference's torch-CPU op sequence (anomaly/models/models.py:649-651: subtract,
+                                 square, sum over the embedding dim in torch's CPU order), so that the distance logits are
+                                 bit-identical to the reference's on identical embeddings.  Slower; for verification and for
+                                 the tiny stride-8 maps of the anomaly path. */
 } dml_head_params;
 
 DML_API int dml_head_forward(const dml_head_params* p, dml_stream_t stream);

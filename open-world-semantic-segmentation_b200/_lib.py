@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libdml_b200.so")
 
 DML_OK = 0
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 c_f32p = C.c_void_p
 c_void_p = C.c_void_p
@@ -34,7 +34,7 @@ class HeadParams(C.Structure):
         ("features_nhwc", C.c_void_p), ("novel_dist", C.c_void_p), ("minmax", C.c_void_p),
         ("want_eds_minmax", C.c_int32), ("want_msp_minmax", C.c_int32),
         ("gt_u8", C.c_void_p), ("gt_i64", C.c_void_p), ("confusion", C.c_void_p),
-        ("conf_rows", C.c_int32), ("conf_cols", C.c_int32),
+        ("conf_rows", C.c_int32), ("conf_cols", C.c_int32), ("reference_order", C.c_int32),
     ]
 
 

@@ -97,7 +97,9 @@ def eval_ood_measure(conf, seg_label, cfg, mask=None):
 
 @dataclass
 class BatchEval:
-    """Device-resident results of one batch (no host synchronisation until ``.host()``)."""
+    """Device-resident results of one batch (no host synchronisation until ``.host()``).
+    ``per_image`` / ``stats`` are private copies; ``label`` / ``conf`` / ``msp`` / ``confusion`` are the evaluator's
+    reused output buffers and are only valid until its next call (clone them to keep a batch)."""
     label: torch.Tensor                 # [B,H,W] uint8 argmax prediction
     conf: Optional[torch.Tensor]        # [B,H,W] normalised EDS (the map the reference ranks), if requested
     msp: Optional[torch.Tensor]         # [B,H,W] raw max-softmax, if requested
@@ -152,7 +154,7 @@ class EmbeddingEvaluator:
         res, stats = ood.eval_segments(out.eds, B, Hh * Ww, gt=gt, out_labels=self.out_labels, score_kind=0,
                                        minmax=out.minmax, minmax_slot=0, conf_out=conf,
                                        recall_level=self.recall_level, workspace=self._ws)
-        return BatchEval(out.label, conf, out.msp, out.confusion, res, stats)
+        return BatchEval(out.label, conf, out.msp, out.confusion, res.clone(), stats.clone())
 
 
 class MultiScaleEvaluator(EmbeddingEvaluator):
@@ -165,13 +167,18 @@ class MultiScaleEvaluator(EmbeddingEvaluator):
     for its ten full-resolution interpolations and read-modify-write accumulations."""
 
     def __call__(self, emb_list, gt: torch.Tensor, confusion: Optional[torch.Tensor] = None,
-                 inputs_are_logits: bool = False, reciprocal_average: bool = False) -> BatchEval:
+                 inputs_are_logits: bool = False, reciprocal_average: bool = False,
+                 reference_order: bool = False) -> BatchEval:
+        """``reference_order``: round the stride-8 distance logits exactly like the reference's torch-CPU ops
+        (``dml_head(..., reference_order=True)``; K < 16): with the bit-exact upsample / average / EDS arithmetic of
+        the fused kernel, pred and conf are then bit-identical to the CPU reference's on identical embeddings."""
         B, Hh, Ww = gt.shape
         dev = gt.device
         if inputs_are_logits:
             z_list = emb_list
         else:
-            z_list = [H.dml_head(e, magnitude=self.magnitude, want_logits=True, label_dtype=None).logits for e in emb_list]
+            z_list = [H.dml_head(e, magnitude=self.magnitude, want_logits=True, label_dtype=None,
+                                 reference_order=reference_order).logits for e in emb_list]
         if self._out is not None and (self._out.label.shape != (B, Hh, Ww) or self._out.label.device != dev):
             self._out = None
         if self._ws is None or self._ws.device != dev:
@@ -188,7 +195,7 @@ class MultiScaleEvaluator(EmbeddingEvaluator):
         res, stats = ood.eval_segments(out.eds, B, Hh * Ww, gt=gt, out_labels=self.out_labels, score_kind=0,
                                        minmax=out.minmax, minmax_slot=0, conf_out=conf,
                                        recall_level=self.recall_level, workspace=self._ws)
-        return BatchEval(out.label, conf, out.msp, out.confusion, res, stats)
+        return BatchEval(out.label, conf, out.msp, out.confusion, res.clone(), stats.clone())
 
 
 def summarize(confusion: np.ndarray, per_image_vals: np.ndarray):

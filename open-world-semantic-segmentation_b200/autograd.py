@@ -52,9 +52,20 @@ class _DmlLoss(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, target, centers, magnitude, alpha, beta, ignore_index, is_logits):
         require_cuda(x, "x")
+        require_cuda(target, "target")
+        # the C ABI takes raw const float* / label pointers: anything else (fp16 / bf16 under autocast, float64,
+        # a target of another size) must be rejected or converted HERE, not read out of bounds by the kernel
+        if x.dim() != 4:
+            raise ValueError("x must be a [B,D,H,W] tensor")
+        if x.dtype != torch.float32:
+            if x.dtype not in (torch.float16, torch.bfloat16, torch.float64):
+                raise ValueError(f"x must be a floating-point tensor, got {x.dtype}")
+            x = x.float()                      # differentiable cast: the gradient returns in the caller's dtype
         x = x.contiguous()
         target = target.contiguous()
         B, D, Hh, Ww = x.shape
+        if target.numel() != B * Hh * Ww:
+            raise ValueError(f"target must hold B*H*W = {B * Hh * Ww} labels, got {tuple(target.shape)}")
         dev = x.device
         mu = None if centers is None else centers.to(device=dev, dtype=torch.float32).contiguous()
         K = D if mu is None else mu.shape[0]

@@ -137,11 +137,12 @@ int dml_head_forward(const dml_head_params* p, dml_stream_t stream_) {
     if (p->conf_rows < 1 || p->conf_cols < 1 || p->conf_rows * p->conf_cols > HEAD_MAX_CONF_BINS) return DML_ERR_INVALID_ARG;
   }
   if (p->B > 65535) return DML_ERR_INVALID_ARG;
+  if (p->reference_order && (mode != HEAD_IDENT || p->D >= 16 || !p->logits)) return DML_ERR_INVALID_ARG;
   const long long hw = (long long)p->H * p->W;
   if (p->B == 0 || hw == 0) return DML_OK;
 
   HeadArgs a = {};
-  a.x = p->x; a.mu = p->mu; a.diag_m = p->diag_m;
+  a.x = p->x; a.mu = p->mu; a.diag_m = p->diag_m; a.ref_order = p->reference_order ? 1 : 0;
   a.msp_scale = 2.0f * p->diag_m * 1.4426950408889634f;
   a.first = p->score_first_class; a.clamp = p->eds_clamp;
   a.mu_novel = p->mu_novel; a.n_novel = p->n_novel; a.novel_base = p->novel_label_base; a.novel_thr = p->novel_thr;

@@ -36,6 +36,7 @@ struct HeadArgs {
   float diag_m;
   float msp_scale;  // 2 * diag_m * log2(e): softmax over z_k == softmax over 2 m x_k when mu = m I
   int first;
+  int ref_order;    // IDENT + logits only: evaluate d_k in the op order of the reference's torch-CPU code (bit-exact parity mode)
   float clamp;
   const double* mu_novel;
   int n_novel, novel_base;
@@ -477,9 +478,13 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_kernel(const HeadArgs a) {
   float* lg = nullptr;
   if constexpr (EXTRA && !LOGITS) lg = (om & OUT_LOGITS) ? a.logits + ((long long)b * K) * a.HW + p0 : nullptr;
 
+  // esum1 accumulates the score classes in index order starting from the first one -- ((d_0 + d_1) + d_2) + ... --
+  // the order torch.sum(scores, dim=1) uses on the class planes (anomaly/eval_ood_traditional.py:302), so that the
+  // EDS map is bit-identical to the reference's on identical logits
   auto visit = [&](int k, int v, float dk) {
     if (k == 0) {
       d0[v] = dk;
+      esum1[v] = skip0 ? 0.f : dk;
     } else {
       if (dk < dmin1[v]) { dmin1[v] = dk; arg1[v] = k; }
       esum1[v] += dk;
@@ -517,6 +522,39 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_kernel(const HeadArgs a) {
         for (int j = 0; j < NG; ++j) outer[j][v] = pre[j] + suf[j];
       }
     }
+    bool ref_done = false;
+    if constexpr (EXTRA && D < 16) {
+      if (a.ref_order) {
+        // Parity mode: z_k = -sum_d (x_d - mu_kd)^2 exactly as the reference's torch-CPU ops round it
+        // (anomaly/models/models.py:649-651): subtract (x - 0 is exact), square, then torch's CPU sum over a
+        // contiguous inner dim of D < 16 floats, one rounded add at a time: for 8 <= D < 16 the tail elements 8 .. D-1
+        // first, then 0 .. 7; for D < 8 element 0, then the tail 4 .. D-1, then 1 .. 3 (recovered by probing the build
+        // in this image and pinned by tests/test_head_reference_order.py); no FMA contraction.
+        ref_done = true;
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+          FVec<VEC> z;
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) {
+            float acc = 0.f;
+#pragma unroll
+            for (int i = 0; i < D; ++i) {
+              int d;
+              if constexpr (D >= 8) d = i < D - 8 ? 8 + i : i - (D - 8);
+              else if constexpr (D > 4) d = i == 0 ? 0 : (i <= D - 4 ? 3 + i : i - (D - 4));
+              else d = i;
+              const float t = (d == k) ? __fsub_rn(x[d][v], a.diag_m) : x[d][v];
+              const float sq = __fmul_rn(t, t);
+              acc = (i == 0) ? sq : __fadd_rn(acc, sq);
+            }
+            visit(k, v, acc);
+            z.v[v] = -acc;
+          }
+          if (lg && active) st_stream<VEC>(lg + (long long)k * a.HW, z);
+        }
+      }
+    }
+    if (!ref_done) {
 #pragma unroll
     for (int k = 0; k < D; ++k) {
       const int j = k >> 2;
@@ -537,6 +575,7 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_kernel(const HeadArgs a) {
       if constexpr (EXTRA)
         if (lg && active) st_stream<VEC>(lg + (long long)k * a.HW, z);
     }
+    }  // !ref_done
     // softmax_k(z) == softmax_k(2 m x_k) when mu = m I (z_k - z_j = 2 m (x_k - x_j) exactly), so the
     // max-softmax is 1 / sum_k exp2(c x_k - c x_ext), c = 2 m log2(e), x_ext the max (m > 0) / min (m < 0).
     if (want_msp) {
@@ -626,7 +665,7 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_kernel(const HeadArgs a) {
     label[v] = zero_wins ? 0 : arg1[v];
     dbest[v] = zero_wins ? d0[v] : dmin1[v];
     smin[v] = (skip0 && K > 1) ? dmin1[v] : dbest[v];
-    float e = (skip0 && K > 1) ? esum1[v] : d0[v] + esum1[v];
+    float e = (skip0 && K == 1) ? d0[v] : esum1[v];
     if (a.clamp > 0.f) e = (e >= a.clamp) ? a.clamp : e;
     eds[v] = e;
     mspv[v] = want_msp ? (1.0f / ssum[v]) : 0.f;

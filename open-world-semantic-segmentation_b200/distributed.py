@@ -49,10 +49,14 @@ class CudaOps:
     # conf / gt -> packed keys (int32 view of the u32 keys), n_pos
     def make_keys(self, conf, gt, out_labels, key_base):
         from ._lib import check, lib, ptr, stream_ptr
+        if conf.dtype != torch.float32:
+            raise ValueError("conf must be float32 (the kernel reads const float*)")
         n = conf.numel()
         keys = self.ws.get("d_keys", 4 * max(n, 1)).view(torch.int32)[:n]
         stats = self.ws.get("d_stats", 32).view(torch.int64)[:4]
         g = gt.contiguous().view(-1)
+        if g.numel() != n or g.dtype not in (torch.uint8, torch.int64):
+            raise ValueError("gt must be uint8 or int64 with one label per conf value")
         with torch.cuda.device(self.device):
             check(lib().dml_ood_keygen(ptr(conf.contiguous().view(-1)), None, 0, None,
                                        ptr(g) if g.dtype == torch.uint8 else None, ptr(g) if g.dtype == torch.int64 else None,

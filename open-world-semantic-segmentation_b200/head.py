@@ -55,7 +55,8 @@ def dml_head(x: torch.Tensor, centers: Optional[torch.Tensor] = None, magnitude:
              exclude_back: bool = False, novel: Optional[torch.Tensor] = None, novel_label_base: int = 16,
              novel_thr: float = NOVEL_THRESHOLD, want_novel_dist: bool = False,
              gt: Optional[torch.Tensor] = None, confusion: Optional[torch.Tensor] = None,
-             confusion_shape: Optional[tuple] = None, out: Optional[HeadOutput] = None) -> HeadOutput:
+             confusion_shape: Optional[tuple] = None, out: Optional[HeadOutput] = None,
+             reference_order: bool = False) -> HeadOutput:
     """One pass over ``x`` [B,D,H,W] (fp32, CUDA, contiguous NCHW).
 
     input_is_logits: ``x`` already holds the logits z [B,K,H,W] (anomaly path: stride-8 distances
@@ -68,6 +69,9 @@ def dml_head(x: torch.Tensor, centers: Optional[torch.Tensor] = None, magnitude:
              [0, rows) ignored); ``confusion`` is an int64 [rows, cols] accumulator (created
              from ``confusion_shape`` when None).
     ``out`` lets callers reuse output buffers (CUDA-graph friendly).
+    reference_order: parity mode (``centers`` = m*I, D < 16, logits requested): every logit is rounded exactly like
+             the reference's torch-CPU op sequence (anomaly/models/models.py:649-651), so the logits -- and everything
+             derived from them -- are bit-identical to the reference's on identical embeddings.
     """
     require_cuda(x, "x")
     if x.dtype != torch.float32 or x.dim() != 4:
@@ -105,6 +109,10 @@ def dml_head(x: torch.Tensor, centers: Optional[torch.Tensor] = None, magnitude:
         want_logits = False
     p.score_first_class = 1 if exclude_back else 0
     p.eds_clamp = eds_clamp
+    if reference_order:
+        if mu is not None or input_is_logits or not want_logits or D >= 16:
+            raise ValueError("reference_order needs m*I prototypes, D < 16 and want_logits=True")
+        p.reference_order = 1
     if novel is not None:
         novel = novel.to(device=dev, dtype=torch.float64).contiguous().view(-1, D)
         p.mu_novel, p.n_novel = novel.data_ptr(), novel.shape[0]

@@ -22,7 +22,10 @@ def class_sums(x: torch.Tensor, labels: torch.Tensor, n_cls: int, nhwc: bool = F
     x: [B,D,H,W] (``nhwc=False``) or [B,H,W,D] (``nhwc=True``) fp32 CUDA; labels [B,H,W] uint8/int64
     (labels outside [0, n_cls) are skipped).  Returns (sums [B,n_cls,D] float64, counts [B,n_cls] int64)."""
     require_cuda(x, "x")
-    x = x.contiguous()
+    require_cuda(labels, "labels")
+    if x.dim() != 4 or not x.is_floating_point():
+        raise ValueError("x must be a 4-D floating-point tensor")
+    x = x.float().contiguous()               # the kernel reads const float*
     labels = labels.contiguous()
     if labels.dtype not in (torch.uint8, torch.int64):
         labels = labels.to(torch.int64)
