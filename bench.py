@@ -44,7 +44,11 @@ def parse_args():
     ap.add_argument("--height", type=int, default=720)
     ap.add_argument("--width", type=int, default=1280)
     ap.add_argument("--classes", type=int, default=13)
-    ap.add_argument("--chunk", type=int, default=int(os.environ.get("DML_BENCH_CHUNK", "50")), help="images per kernel batch")
+    ap.add_argument("--chunk", type=int, default=int(os.environ.get("DML_BENCH_CHUNK", "0")),
+                    help="images per kernel batch (0 = 74 for --metric-method rank: two CTAs of the rank kernel per image on 148 SMs; 50 for sort)")
+    ap.add_argument("--metric-method", default=os.environ.get("DML_BENCH_METHOD", "rank"), choices=["rank", "sort"],
+                    help="per-image exact metrics: minority-rank path (positives sorted, negatives located among them in the "
+                         "pass that writes the maps) or the full radix sort of every (score, label) pair")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--cpu-images", type=int, default=0, help="images in the CPU-baseline sample (0 = one per worker)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -261,7 +265,7 @@ class Pipeline:
         self.k, self.h, self.w = args.classes, args.height, args.width
         self.n = args.images
         self.hw = self.h * self.w
-        self.chunk = min(args.chunk, self.n)
+        self.chunk = min(args.chunk or (74 if args.metric_method == "rank" else 50), self.n)
         self.bounds = [(s, min(s + self.chunk, self.n)) for s in range(0, self.n, self.chunk)]
         n, k, h, w = self.n, self.k, self.h, self.w
         f32, u8 = torch.float32, torch.uint8
@@ -314,7 +318,7 @@ class Pipeline:
         res, stats = ood.eval_segments(self.eds[s:e], nb, self.hw, gt=gt, out_labels=(self.k,), score_kind=0,
                                        minmax=self.minmax[s:e], minmax_slot=0, conf_out=self.conf[s:e],
                                        workspace=self.ws_img, msp=self.msp[s:e], msp_norm_out=self.mmsp_c[:nb],
-                                       mix_out=self.mix_c[:nb], pool=self.pool)
+                                       mix_out=self.mix_c[:nb], pool=self.pool, method=self.args.metric_method)
         if time_head:
             ev2.record()
             self.metric_events.append((ev1, ev2))

@@ -323,6 +323,28 @@ DML_API int dml_ood_scan_range(const uint32_t* sorted_keys, int64_t n, const lon
                        double recall_level, void* workspace, size_t workspace_bytes, void* partial_out,
                        dml_stream_t stream);
 
+/* ------------------------------------------------------------------------------------ *
+ * (d') Exact metrics without sorting the negatives ("minority rank" path).
+ *
+ * Same inputs, outputs and semantics as dml_ood_keygen + dml_ood_eval_segments (anomaly/anom_utils.py:25-78,
+ * anomaly/eval_ood_traditional.py:128-148), for the usual case that the positives (OOD pixels) are few: per segment
+ * the positives' keys are gathered and sorted in shared memory, and ONE pass over all pairs -- which also writes the
+ * normalised conf / MMSP / mix maps and, if `keys_out` != NULL, the packed ranking keys (for a later pooled metric) --
+ * locates every negative among the segment's distinct positive scores and counts it; a scan over the positive groups
+ * yields AUROC / AUPR / FPR@recall.  AUROC and FPR are bit-identical to the sort path (integer counting), AUPR differs
+ * by float64 summation order only; dml_ood_result.n_groups is -1 (negative-only score groups are not enumerated).
+ * `pos_capacity` (1 .. 32768): positives per segment this call can hold.  A segment with more is NOT evaluated:
+ * its result is NaN and seg_stats[seg][3] = 1 -- evaluate it with dml_ood_keygen + dml_ood_eval_segments instead.
+ * seg_stats (device, [n_seg,4] int64) = (n_pos, n_nan, n_out_of_window, overflow flag).
+ * workspace: dml_ood_rank_workspace_bytes(n_seg, pos_capacity).  All pointers device. */
+DML_API size_t dml_ood_rank_workspace_bytes(int32_t n_seg, int32_t pos_capacity);
+DML_API int dml_ood_rank_segments(const float* values, const float* minmax, int32_t minmax_slot, float* conf_out,
+                          const uint8_t* gt_u8, const int64_t* gt_i64, uint64_t out_label_mask, const uint8_t* pos_u8,
+                          int32_t score_kind, uint32_t key_base, int32_t n_seg, int64_t seg_len, uint32_t* keys_out,
+                          long long* seg_stats, const float* msp, float* msp_norm_out, float* mix_out, float lambda,
+                          float thr, int32_t pos_capacity, double recall_level, void* workspace, size_t workspace_bytes,
+                          dml_ood_result* results, dml_stream_t stream);
+
 /* "partition" exchange mode of the multi-GPU pooled metric: scatter UNSORTED packed keys into n_buckets
  * contiguous key ranges (one per rank), ship range r to rank r, sort only what is received -- one partition
  * pass instead of one full local sort.  bucket(key) = #{ j : key >= bounds[j] } with `bounds` a DEVICE

@@ -109,6 +109,11 @@ SIGNATURES = {
                                     C.c_size_t, C.c_void_p]),
     "dml_ood_lower_bound": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "dml_ood_count_positive": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "dml_ood_rank_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
+    "dml_ood_rank_segments": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64,
+                                        C.c_void_p, C.c_int32, C.c_uint32, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p,
+                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_int32, C.c_double,
+                                        C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
     "dml_ood_scan_range": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_double, C.c_void_p, C.c_size_t,
                                      C.c_void_p, C.c_void_p]),
 }

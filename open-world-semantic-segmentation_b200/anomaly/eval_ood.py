@@ -124,8 +124,12 @@ class EmbeddingEvaluator:
 
     def __init__(self, num_class: int = 13, out_labels: Sequence[int] = (13,), clamp: float = H.CLAMP_ANOMALY,
                  magnitude: float = H.DEFAULT_MAGNITUDE, want_msp: bool = True, store_conf: bool = True,
-                 recall_level: float = 0.95):
+                 recall_level: float = 0.95, method: str = "sort", pos_capacity: int = ood.POS_CAPACITY_DEFAULT):
+        """``method`` / ``pos_capacity``: see ``ood.eval_segments`` ("rank": the minority-rank path for images whose
+        OOD pixels are few; "auto": rank with a checked fall-back to the sort path)."""
         self.K = num_class
+        self.method = method
+        self.pos_capacity = pos_capacity
         self.out_labels = tuple(out_labels)
         self.clamp = clamp
         self.magnitude = magnitude
@@ -153,7 +157,8 @@ class EmbeddingEvaluator:
             conf = self._conf
         res, stats = ood.eval_segments(out.eds, B, Hh * Ww, gt=gt, out_labels=self.out_labels, score_kind=0,
                                        minmax=out.minmax, minmax_slot=0, conf_out=conf,
-                                       recall_level=self.recall_level, workspace=self._ws)
+                                       recall_level=self.recall_level, workspace=self._ws, method=self.method,
+                                       pos_capacity=self.pos_capacity)
         return BatchEval(out.label, conf, out.msp, out.confusion, res.clone(), stats.clone())
 
 
@@ -194,7 +199,8 @@ class MultiScaleEvaluator(EmbeddingEvaluator):
             conf = self._conf
         res, stats = ood.eval_segments(out.eds, B, Hh * Ww, gt=gt, out_labels=self.out_labels, score_kind=0,
                                        minmax=out.minmax, minmax_slot=0, conf_out=conf,
-                                       recall_level=self.recall_level, workspace=self._ws)
+                                       recall_level=self.recall_level, workspace=self._ws, method=self.method,
+                                       pos_capacity=self.pos_capacity)
         return BatchEval(out.label, conf, out.msp, out.confusion, res.clone(), stats.clone())
 
 

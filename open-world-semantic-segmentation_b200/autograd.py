@@ -58,9 +58,7 @@ class _DmlLoss(torch.autograd.Function):
         if x.dim() != 4:
             raise ValueError("x must be a [B,D,H,W] tensor")
         if x.dtype != torch.float32:
-            if x.dtype not in (torch.float16, torch.bfloat16, torch.float64):
-                raise ValueError(f"x must be a floating-point tensor, got {x.dtype}")
-            x = x.float()                      # differentiable cast: the gradient returns in the caller's dtype
+            raise ValueError(f"x must be float32, got {x.dtype} (dml_loss() upcasts fp16 / bf16 / fp64 inputs)")
         x = x.contiguous()
         target = target.contiguous()
         B, D, Hh, Ww = x.shape
@@ -110,6 +108,10 @@ def dml_loss(x: torch.Tensor, target: torch.Tensor, *, centers: Optional[torch.T
         m = H.scaled_identity_magnitude(centers)
         if m is not None and centers.shape[0] == x.shape[1]:
             centers, magnitude = None, m
+    if x.dtype != torch.float32:
+        if not x.is_floating_point():
+            raise ValueError(f"x must be a floating-point tensor, got {x.dtype}")
+        x = x.float()        # differentiable cast (autocast fp16 / bf16, float64): the kernels compute in fp32
     loss, parts = _DmlLoss.apply(x, target, centers, float(magnitude), float(alpha), float(beta), int(ignore_index),
                                  bool(input_is_logits))
     return (loss, parts) if return_parts else loss

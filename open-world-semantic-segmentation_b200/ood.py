@@ -14,12 +14,18 @@ from typing import Iterable, Optional, Sequence
 import numpy as np
 import torch
 
-from ._lib import OOD_RESULT_WORDS, check, lib, ptr, require_cuda, stream_ptr
+from ._lib import OOD_RESULT_WORDS, DmlError, check, lib, ptr, require_cuda, stream_ptr
 
 RECALL_LEVEL_DEFAULT = 0.95       # anomaly/anom_utils.py:4
 KEY_BASE_NONNEG = 0x80000000      # sortable image of +0.0: any conf >= 0 fits the 31-bit window
 PARTIAL_WORDS = 10                # u64 auroc_num, f64 ap_sum, i64 a_idx,a_tps,a_fps, b_tps,b_idx,b_fps, n_groups, reserved
 NO_B = (1 << 63) - 1
+POS_CAPACITY_DEFAULT = 16384      # positives per segment of the minority-rank path (<= 32768: shared-memory sort)
+
+
+class MinorityOverflow(DmlError):
+    """A segment evaluated with ``method="rank"`` holds more positives than ``pos_capacity``: its result is NaN.
+    Re-evaluate with ``method="sort"`` (no limit) or ``method="auto"`` (checks and falls back by itself)."""
 
 
 def label_mask(out_labels: Iterable[int]) -> int:
@@ -74,6 +80,7 @@ class KeyPool:
     def reset(self):
         self.n = 0
         self.signature = None
+        self.hist_ok = True      # every contribution so far also left its digit histograms (method="sort" batches)
         self.stats.zero_()
 
     def _take(self, n: int, signature) -> torch.Tensor:
@@ -97,7 +104,7 @@ class KeyPool:
         results = self.ws.get("pool_results", 8 * OOD_RESULT_WORDS).view(torch.float64)[:OOD_RESULT_WORDS].view(1, OOD_RESULT_WORDS)
         with torch.cuda.device(self.device):
             check(lib().dml_ood_eval_segments(ptr(self.keys), ptr(self.stats), 1, self.capacity, recall_level,
-                                              ptr(self.scratch), self.scratch.numel(), 1, ptr(results),
+                                              ptr(self.scratch), self.scratch.numel(), 1 if self.hist_ok else 0, ptr(results),
                                               stream_ptr(self.device)), "dml_ood_eval_segments")
         return results, self.stats
 
@@ -107,6 +114,9 @@ def _raise_on_bad_stats(stats: np.ndarray, what: str):
         raise ValueError("Input contains NaN.")           # sklearn's validation in the reference path
     if (stats[:, 2] > 0).any():
         raise ValueError(f"{what}: ranking keys outside the packed 31-bit window (wrong key_base)")
+    if stats.shape[1] > 3 and (stats[:, 3] > 0).any():
+        raise MinorityOverflow(f"{what}: {int((stats[:, 3] > 0).sum())} segment(s) hold more positives than pos_capacity "
+                               "(method='rank'); use method='sort' or 'auto'")
 
 
 def eval_segments(values: torch.Tensor, n_seg: int, seg_len: int, *, gt: Optional[torch.Tensor] = None,
@@ -115,7 +125,8 @@ def eval_segments(values: torch.Tensor, n_seg: int, seg_len: int, *, gt: Optiona
                   conf_out: Optional[torch.Tensor] = None, recall_level: float = RECALL_LEVEL_DEFAULT,
                   workspace: Optional[OodWorkspace] = None, msp: Optional[torch.Tensor] = None,
                   msp_norm_out: Optional[torch.Tensor] = None, mix_out: Optional[torch.Tensor] = None,
-                  lam: float = 50.0, thr: float = 0.2, pool: Optional[KeyPool] = None):
+                  lam: float = 50.0, thr: float = 0.2, pool: Optional[KeyPool] = None, method: str = "sort",
+                  pos_capacity: int = POS_CAPACITY_DEFAULT):
     """Evaluate ``n_seg`` independent segments of ``seg_len`` (score, label) pairs each.
 
     values: flat fp32 CUDA tensor (n_seg*seg_len): a ``conf`` map ranked as score = -conf
@@ -128,17 +139,30 @@ def eval_segments(values: torch.Tensor, n_seg: int, seg_len: int, *, gt: Optiona
             EDS/MMSP mix (anomaly/eval_ood_traditional.py:434-435,447-448) written in the same pass.
     pool:   a ``KeyPool`` collecting the keys / digit histograms / counts of this call for a later pooled
             evaluation over all calls (``pool.evaluate()``).
+    method: "sort" = radix sort of every pair + tie-aware scan (no limits); "rank" = the minority-rank path
+            (``dml_ood_rank_segments``: only the positives are sorted, every negative is located among them in the
+            one pass that also writes the maps; 3-4x less work when positives are rare) -- segments with more than
+            ``pos_capacity`` positives come back NaN with ``stats[:, 3] = 1`` and ``results_to_host`` raises
+            ``MinorityOverflow``; "auto" = "rank", then ONE host synchronisation to look at the overflow flags and a
+            re-evaluation with "sort" if any is set (the inputs must still be intact, so not for in-place pipelines).
+            AUROC / FPR are bit-identical between the methods, AUPR differs by float64 summation order;
+            ``results[:, 6]`` (n_groups) is -1 on the rank path.
     Returns (results, stats): device tensors -- results float64 [n_seg,7] viewed as
     (auroc, aupr, fpr, n_pos, n_neg, n_nan, n_groups; the last four are int64 bit patterns),
     stats int64 [n_seg,4] = (n_pos, n_nan, n_out_of_window, 0).  No host synchronisation.
     """
     require_cuda(values, "values")
+    if method not in ("sort", "rank", "auto"):
+        raise ValueError("method must be 'sort', 'rank' or 'auto'")
     dev = values.device
     values = values.contiguous().view(-1)
     if values.dtype != torch.float32 or values.numel() != n_seg * seg_len:
         raise ValueError("values must be float32 with n_seg*seg_len elements")
     ws = workspace or OodWorkspace(dev)
     n = n_seg * seg_len
+    if method != "sort" and n > 0:
+        return _eval_segments_rank(values, n_seg, seg_len, gt, out_labels, positive, score_kind, key_base, minmax, minmax_slot,
+                                   conf_out, recall_level, ws, msp, msp_norm_out, mix_out, lam, thr, pool, method, pos_capacity)
     keys = ws.get("keys", 4 * n) if pool is None else pool._take(n, (int(key_base), int(score_kind)))
     stats = ws.get("stats", 32 * max(n_seg, 1)).view(torch.int64)[: 4 * n_seg].view(n_seg, 4)
     results = ws.get("results", 8 * OOD_RESULT_WORDS * max(n_seg, 1)).view(torch.float64)[: OOD_RESULT_WORDS * n_seg]
@@ -184,6 +208,63 @@ def eval_segments(values: torch.Tensor, n_seg: int, seg_len: int, *, gt: Optiona
                                                 ptr(pool.stats), 1 if pool.n == n else 0, s), "dml_ood_pool_histograms")
         check(lib().dml_ood_eval_segments(ptr(keys), ptr(stats), n_seg, seg_len, recall_level, ptr(scratch),
                                           scratch.numel(), 1 if fused_hist else 0, ptr(results), s), "dml_ood_eval_segments")
+    return results, stats
+
+
+def _labels_of(gt, positive, n):
+    gt_u8 = gt_i64 = pos_u8 = None
+    if positive is not None:
+        pos_u8 = positive.contiguous().view(-1)
+        if pos_u8.dtype == torch.bool:
+            pos_u8 = pos_u8.view(torch.uint8)
+        if pos_u8.dtype != torch.uint8 or pos_u8.numel() != n:
+            raise ValueError("positive must be uint8/bool with one entry per value")
+    elif gt is not None:
+        g = gt.contiguous().view(-1)
+        if g.numel() != n:
+            raise ValueError("gt must have one entry per value")
+        if g.dtype == torch.uint8:
+            gt_u8 = g
+        elif g.dtype == torch.int64:
+            gt_i64 = g
+        else:
+            raise ValueError("gt must be uint8 or int64")
+    else:
+        raise ValueError("need gt or positive")
+    return gt_u8, gt_i64, pos_u8
+
+
+def _eval_segments_rank(values, n_seg, seg_len, gt, out_labels, positive, score_kind, key_base, minmax, minmax_slot, conf_out,
+                        recall_level, ws, msp, msp_norm_out, mix_out, lam, thr, pool, method, pos_capacity):
+    """``eval_segments`` through ``dml_ood_rank_segments`` (see there)."""
+    dev = values.device
+    n = n_seg * seg_len
+    pos_capacity = int(min(max(pos_capacity, 1), 32768))
+    gt_u8, gt_i64, pos_u8 = _labels_of(gt, positive, n)
+    stats = ws.get("stats", 32 * max(n_seg, 1)).view(torch.int64)[: 4 * n_seg].view(n_seg, 4)
+    results = ws.get("results", 8 * OOD_RESULT_WORDS * max(n_seg, 1)).view(torch.float64)[: OOD_RESULT_WORDS * n_seg]
+    results = results.view(n_seg, OOD_RESULT_WORDS)
+    rws = ws.get("rank_ws", lib().dml_ood_rank_workspace_bytes(n_seg, pos_capacity))
+    pool_mark = (pool.n, pool.signature, pool.hist_ok) if pool is not None else None
+    keys = pool._take(n, (int(key_base), int(score_kind))) if pool is not None else None
+    with torch.cuda.device(dev):
+        s = stream_ptr(dev)
+        check(lib().dml_ood_rank_segments(ptr(values), ptr(minmax), minmax_slot, ptr(conf_out), ptr(gt_u8), ptr(gt_i64),
+                                          label_mask(out_labels) if positive is None else 0, ptr(pos_u8), score_kind,
+                                          key_base, n_seg, seg_len, ptr(keys), ptr(stats), ptr(msp), ptr(msp_norm_out),
+                                          ptr(mix_out), lam, thr, pos_capacity, recall_level, ptr(rws), rws.numel(),
+                                          ptr(results), s), "dml_ood_rank_segments")
+        if method == "auto" and bool((stats[:, 3] != 0).any().item()):       # the one host synchronisation of "auto"
+            if pool is not None:
+                pool.n, pool.signature, pool.hist_ok = pool_mark
+            return eval_segments(values, n_seg, seg_len, gt=gt, out_labels=out_labels, positive=positive,
+                                 score_kind=score_kind, key_base=key_base, minmax=minmax, minmax_slot=minmax_slot,
+                                 conf_out=conf_out, recall_level=recall_level, workspace=ws, msp=msp,
+                                 msp_norm_out=msp_norm_out, mix_out=mix_out, lam=lam, thr=thr, pool=pool, method="sort")
+        if pool is not None:
+            pool.hist_ok = False       # this batch left keys and counts, no digit histograms
+            check(lib().dml_ood_pool_histograms(None, 0, ptr(stats), n_seg, seg_len, None, 0, pool.capacity, ptr(pool.stats),
+                                                1 if pool.n == n else 0, s), "dml_ood_pool_histograms")
     return results, stats
 
 
