@@ -54,6 +54,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-pooled", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the bounded side measurements (roofline.extra, strong scaling, config 5, pooled self-check)")
+    ap.add_argument("--config5-images", type=int, default=4000, help="total images of the metric scaling sweep (BASELINE.json configs[4]; N > 1 only, 0 = skip)")
     ap.add_argument("--pooled-keys", default=os.environ.get("DML_BENCH_POOLED_KEYS", "reuse"), choices=["reuse", "regenerate"],
                     help="pooled metric: reuse the ranking keys / digit histograms of the per-image pass (ood.KeyPool), or "
                          "regenerate them from the conf maps in a second pass")
@@ -140,11 +142,57 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------------
 # CPU baseline: the reference's algorithm (oracle port) on the host cores
 # --------------------------------------------------------------------------------------------
-def _cpu_process_image(O, x, gt, k):
-    """One image through the reference's per-image hot path on ONE core:
-    distance head (network/utils.py:89-117 op sequence) -> argmax -> dissum / MMSP / mix maps
-    (eval_ood_traditional.py:218,302-305,434-448) -> per-image AUROC/AUPR/FPR via scikit-learn +
-    fpr_and_fdr_at_recall (anom_utils.py:67-78) -> accuracy / IoU counts (utils.py:128-156)."""
+def _load_reference():
+    """The reference's own callables for the path, imported from the UNMODIFIED copy under baseline/_ref
+    (oracle/install_reference.py) through the shims of oracle/ref_loader.py; None when the copy is absent."""
+    os.environ.setdefault("DML_REF_FORCE_CPU", "1")     # `.cuda()` calls of the reference stay on the host in this arm
+    try:
+        from oracle import ref_loader
+        if ref_loader.reference_root() is None:
+            return None
+        import contextlib, io
+        with contextlib.redirect_stdout(io.StringIO()):
+            with ref_loader.reference("anomaly"):
+                import anom_utils, eval_ood_traditional as E, utils as U
+                ref = {"E": E, "accuracy": U.accuracy, "intersectionAndUnion": U.intersectionAndUnion, "anom_utils": anom_utils,
+                       "cfg": ref_loader.CfgNode(OOD=ref_loader.CfgNode(out_labels=(13,)))}
+            with ref_loader.reference("DeepLabV3Plus-Pytorch"):
+                import network.utils as NU
+                ref["model_cls"] = NU._SimpleSegmentationModel_embedding
+        return ref
+    except Exception as exc:      # fall back to the oracle port, say so in the JSON line
+        return {"error": repr(exc)}
+
+
+def _cpu_process_image(O, x, gt, k, ref=None):
+    """One image through the reference's per-image hot path on ONE core.
+    With `ref` (baseline/_ref): the reference's own code -- `_SimpleSegmentationModel_embedding.forward`
+    (network/utils.py:84-118) around identity backbone / classifier modules, then the score lines of `evaluate()`
+    replayed with its own helpers (`Normalizatoin`, `Coefficient_map`, `eval_ood_measure` -> `anom_utils.get_and_print_results`,
+    eval_ood_traditional.py:101-106,128-148,218,302-305,434-450) and `utils.accuracy` / `intersectionAndUnion`.
+    Without: the oracle port of the same lines."""
+    if ref is not None and "model_cls" in ref:
+        import torch
+        import torch.nn as nn
+        E = ref["E"]
+        model = ref["model_cls"](nn.Identity(), nn.Identity())
+        with torch.no_grad():
+            scores, _, _ = model(x)
+        _, pred = torch.max(scores, dim=1)
+        pred = pred.squeeze(0).numpy()
+        dis_sum = -torch.sum(scores, dim=1).squeeze(0).numpy()
+        dis_sum[dis_sum >= 400] = 400
+        dis_sum = E.Normalizatoin(dis_sum)
+        prob_map = np.max(nn.functional.softmax(scores, dim=1).squeeze().numpy(), axis=0)
+        prob_map = E.Normalizatoin(prob_map)
+        coef = E.Coefficient_map(dis_sum, 0.2)
+        conf = coef * dis_sum + (1 - coef) * prob_map
+        conf = dis_sum
+        ref["cfg"].OOD.out_labels = (k,)
+        res = E.eval_ood_measure(conf, gt, ref["cfg"])
+        ref["accuracy"](pred, gt)
+        ref["intersectionAndUnion"](pred, gt, k)
+        return conf, res
     z = O.distance_logits(x, O.make_centers(k))
     pred = O.argmax_label(z)[0]
     conf = O.score_dissum(z, 400.0)
@@ -161,17 +209,20 @@ def _cpu_worker(wid, seeds, k, h, w, barrier, queue):
     import sklearn.metrics  # noqa: F401  (imports and input generation stay outside the timed region)
     from oracle import dml_oracle as O
     torch.set_num_threads(1)
+    ref = _load_reference()
+    if ref is not None and "error" in ref:
+        ref = None
     data = []
     for seed in seeds:
         gen = torch.Generator().manual_seed(seed)
         x, gt = synth_chunk_torch(1, k, h, w, gen, "cpu")
         data.append((x, gt[0].numpy().astype(np.int64)))
-    _cpu_process_image(O, data[0][0][:, :, :8, :8].contiguous(), data[0][1][:8, :8], k) if data else None  # warm caches
+    _cpu_process_image(O, data[0][0][:, :, :8, :8].contiguous(), data[0][1][:8, :8], k, ref) if data else None  # warm caches
     barrier.wait()
     t0 = time.perf_counter()
     out = []
     for x, gt in data:
-        conf, res = _cpu_process_image(O, x, gt, k)
+        conf, res = _cpu_process_image(O, x, gt, k, ref)
         out.append((conf, gt))
     dt = time.perf_counter() - t0
     barrier.wait()   # everyone done: the parent stops its clock here
@@ -200,17 +251,24 @@ def cpu_reference_sample(n_images, k, h, w, workers, pooled=True, seed0=10_000):
     for p in procs:
         p.join()
     t_pool = 0.0
+    ref = _load_reference()
+    kind = "reference" if (ref is not None and "model_cls" in ref) else "port"
     if pooled:
         from oracle import dml_oracle as O
         conf = np.concatenate([c.reshape(-1) for r in results for (c, g) in r[3]])
         gt = np.concatenate([g.reshape(-1) for r in results for (c, g) in r[3]])
         t1 = time.perf_counter()
-        O.eval_ood_measure(conf, gt, (k,), use_sklearn=True)
+        if kind == "reference":
+            ref["cfg"].OOD.out_labels = (k,)
+            ref["E"].eval_ood_measure(conf, gt, ref["cfg"])        # the same reference function over all pixels of the sample
+        else:
+            O.eval_ood_measure(conf, gt, (k,), use_sklearn=True)
         t_pool = time.perf_counter() - t1
     px = n_images * h * w
     per_img = sum(r[1] for r in results) / max(1, sum(r[2] for r in results))
     return t_img + t_pool, px, {"per_image_phase_s": t_img, "pooled_phase_s": t_pool,
-                                "mean_single_core_s_per_image": float(per_img)}
+                                "mean_single_core_s_per_image": float(per_img), "kind": kind,
+                                "reference_load_error": (ref or {}).get("error")}
 
 
 def run_reference(args):
@@ -232,13 +290,18 @@ def run_reference(args):
         times.append(dt)
     ms = 1e3 * float(np.mean(times))
     value = px / (ms * 1e-3) / 1e6
+    kind = detail.pop("kind", "port")
     sample = (f"{n_img} synthetic {h}x{w} images per step ({workers} processes x 1 thread), per-image head+scores+"
-              f"sklearn metrics, then pooled metrics over the sample")
+              f"sklearn metrics, then pooled metrics over the sample; " +
+              ("the reference's own code from baseline/_ref (network/utils.py forward on identity backbone/classifier, "
+               "eval_ood_traditional.py Normalizatoin / Coefficient_map / eval_ood_measure, anom_utils.get_and_print_results, utils.accuracy / "
+               "intersectionAndUnion; the inline score lines of evaluate() replayed around them)" if kind == "reference"
+               else "oracle port (baseline/_ref absent)"))
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": min(args.warmup, 1), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(args), "sample": sample},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "port", "sample": sample, **detail},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": kind, "sample": sample, **detail},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     emit_json_line(line)
@@ -284,7 +347,8 @@ class Pipeline:
         # the per-image pass leaves its packed keys (and, on one GPU, their digit histograms) for the pooled metric
         self.pool = None
         if not args.no_pooled and args.pooled_keys == "reuse":
-            self.pool = ood.KeyPool(n * self.hw, device, workspace=self.ws_pool, histograms=(world == 1))
+            self.pool = ood.KeyPool(n * self.hw, device, workspace=self.ws_pool,
+                                    histograms=(world == 1 and args.metric_method == "sort"))
         self.outs = []
         for (s, e) in self.bounds:
             self.outs.append(H.HeadOutput(label=self.label[s:e], eds=self.eds[s:e], msp=self.msp[s:e],
@@ -293,6 +357,8 @@ class Pipeline:
         self.metric_events = []
         self.pooled_events = []
         self.pooled_result = None
+        self.mean_all_ranks = None
+        self.confusion_all = None
 
     def begin_step(self):
         self.confusion.zero_()
@@ -328,17 +394,31 @@ class Pipeline:
     def pooled(self, gt_all):
         if self.args.no_pooled:
             return
+        rank_mode = self.args.metric_method == "rank"
         if self.world == 1:
             if self.pool is not None:
-                self.pooled_result = self.pool.evaluate()
+                self.pooled_result = self.pool.evaluate(method="rank" if rank_mode else "sort")
             else:
                 self.pooled_result = self.ood.eval_segments(self.conf.view(-1), 1, self.n * self.hw, gt=gt_all.view(-1),
                                                             out_labels=(self.k,), score_kind=0, workspace=self.ws_pool)
         else:
             from dml_b200 import distributed as D
-            ks = (self.pool.keys, self.pool.stats[0]) if self.pool is not None else None
+            ks = None
+            if self.pool is not None:
+                ks = (self.pool.keys, self.pool.stats[0])
+                if rank_mode and self.pool.pos is not None:
+                    ks = ks + (self.pool.pos, self.pool.pos_count)
             self.pooled_result = D.pooled_measures(self.conf.view(-1), gt_all.view(-1), (self.k,), workspace=self.ws_pool,
-                                                   timing=True, keys_and_stats=ks)
+                                                   timing=True, keys_and_stats=ks, mode="rank" if rank_mode else "partition")
+
+    def reduce_across_ranks(self):
+        """the two small collectives of SURVEY.md section 8(e): the reference's aggregate (mean over ALL images of the
+        per-image metrics, eval_ood_traditional.py:569,641) and the summed confusion counts"""
+        if self.world == 1:
+            return
+        from dml_b200 import distributed as D
+        self.mean_all_ranks = D.mean_of_per_image(self.per_image)
+        self.confusion_all = D.allreduce_counts(self.confusion.clone())
 
     def step_resident(self, x_all, gt_all, time_head=False):
         self.begin_step()
@@ -351,7 +431,243 @@ class Pipeline:
         if time_head:
             p1.record()
             self.pooled_events.append((p0, p1))
+        self.reduce_across_ranks()
 
+
+
+# --------------------------------------------------------------------------------------------
+# bounded side measurements carried in the same JSON line (same box, same clocks record)
+# --------------------------------------------------------------------------------------------
+def _timed_ms(torch, fn, iters, warmup=3):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def extra_rooflines(device, peak):
+    """The other configs of BASELINE.json on this box (CUDA events, inputs larger than L2 or L2-flushed by size):
+    config 3 head at the Cityscapes shape, config 4 loss forward / forward+backward and masked class sums, config 1
+    multi-scale head.  Each entry: algorithmic bytes per pixel, ms per launch, achieved GB/s, fraction of the HBM peak."""
+    import torch
+    import dml_b200
+    from dml_b200 import head as H, prototypes
+    out = {}
+    g = torch.Generator(device=device).manual_seed(3)
+
+    def entry(px, bpp, ms, **kw):
+        gbs = px * bpp / ms / 1e6
+        return {"bytes_per_pixel": bpp, "ms": ms, "achieved_GBps": gbs, "frac_of_hbm_peak": gbs / peak,
+                "Mpixel_per_s": px / ms / 1e3, **kw}
+
+    # ---- config 3: DeepLab head, Cityscapes shape, batch 16 (scores-only form: read x 4D + gt 1, write label 1 + EDS 4 + MSP 4)
+    B, D, Hh, Ww = 16, 16, 1024, 2048
+    # the main workload's synthetic recipe at this shape: x = 3 e_c + noise on 64 x 64 class tiles, gt = c (OOD discs = 16)
+    x, gt = synth_chunk_torch(B, D, Hh, Ww, g, device)
+    o = H.HeadOutput()
+    ms = _timed_ms(torch, lambda: H.dml_head(x, magnitude=3.0, want_logits=False, label_dtype=torch.uint8, want_eds=True,
+                                             eds_clamp=1000.0, want_msp=True, want_minmax=True, gt=gt,
+                                             confusion_shape=(D + 1, D), out=o), 10)
+    out["config3_head_cityscapes_16x16x1024x2048"] = entry(B * Hh * Ww, 4 * D + 10, ms, kernel="head_kernel<16,IDENT,2,false>")
+    # the drop-in form of network/utils.py:84-118 (logits + NHWC features returned): read 4D, write logits 4K + features 4D + label 8
+    o2 = H.HeadOutput()
+    ms = _timed_ms(torch, lambda: H.dml_head(x, magnitude=3.0, want_logits=True, label_dtype=torch.int64, want_features=True,
+                                             out=o2), 5)
+    out["config3_head_dropin_logits_features"] = entry(B * Hh * Ww, 4 * D + 4 * D + 4 * D + 8, ms, kernel="head_kernel<16,IDENT,2,true>")
+    del x, gt, o, o2
+    # ---- config 4: few-shot crop 768, K = 17; 20 crops so that the input (802 MB) exceeds L2
+    B, D, S = 20, 17, 768
+    x = torch.randn(B, D, S, S, device=device, generator=g)
+    tl = (S + 63) // 64
+    t64 = torch.randint(0, D, (B, tl, tl), device=device, generator=g).repeat_interleave(64, 1).repeat_interleave(64, 2)
+    t64 = t64[:, :S, :S].contiguous()
+    t64[torch.rand(B, S, S, device=device, generator=g) < 0.1] = 255
+    t8 = t64.to(torch.uint8)
+    t8_iid = torch.randint(0, D, (B, S, S), device=device, generator=g).to(torch.uint8)
+    xg = x.clone().requires_grad_(True)
+    px = B * S * S
+
+    def fwd_bwd():
+        xg.grad = None
+        dml_b200.dml_loss(xg, t64, alpha=0.01, beta=0.01 / 80, ignore_index=255).backward()
+
+    with torch.no_grad():
+        ms_f = _timed_ms(torch, lambda: dml_b200.dml_loss(x, t64, alpha=0.01, beta=0.01 / 80, ignore_index=255), 10)
+        ms_f8 = _timed_ms(torch, lambda: dml_b200.dml_loss(x, t8, alpha=0.01, beta=0.01 / 80, ignore_index=255), 10)
+    ms_fb = _timed_ms(torch, fwd_bwd, 10)
+    out["config4_loss_forward_int64_targets"] = entry(px, 4 * D + 8, ms_f, kernel="loss_kernel<17,IDENT,VEC,false>")
+    out["config4_loss_forward_uint8_targets"] = entry(px, 4 * D + 1, ms_f8, kernel="loss_kernel<17,IDENT,VEC,false>")
+    out["config4_loss_forward_backward"] = entry(px, 12 * D + 16, ms_fb, kernel="loss_kernel fwd + bwd")
+    ms_c = _timed_ms(torch, lambda: prototypes.class_sums(x, t8, 19), 10)
+    out["config4_class_sums_coherent_labels"] = entry(px, 4 * D + 1, ms_c, kernel="class_sums_kernel<17>")
+    ms_i = _timed_ms(torch, lambda: prototypes.class_sums(x, t8_iid, 19), 5)
+    out["config4_class_sums_iid_labels_worst_case"] = entry(px, 4 * D + 1, ms_i, kernel="class_sums_kernel<17>")
+    del x, xg, t64, t8, t8_iid
+    # ---- config 1: anomaly path, 5 stride-8 scales -> 720x1280 (5 stride-8 heads + ONE fused upsample/average/score
+    #      kernel; output-write bound in principle: gt 1 read, label 1 + EDS 4 + MSP 4 written per pixel)
+    B, K, size = 50, 13, (720, 1280)
+    embs = [torch.randn(B, K, h, w, generator=g, device=device) * 0.7 + 1.0
+            for (h, w) in [(38, 67), (47, 84), (57, 100), (66, 117), (71, 125)]]
+    gt = torch.randint(0, K + 1, (B, 12, 20), generator=g, device=device)
+    gt = gt.repeat_interleave(64, 1).repeat_interleave(64, 2)[:, :size[0], :size[1]].contiguous().to(torch.uint8)
+    o, lows = H.HeadOutput(), [H.HeadOutput() for _ in embs]
+    conf = torch.zeros(K + 1, K, dtype=torch.int64, device=device)
+
+    def fused():
+        z = [H.dml_head(e, want_logits=True, label_dtype=None, out=oo).logits for e, oo in zip(embs, lows)]
+        H.dml_multiscale_head(z, size, label_dtype=torch.uint8, want_eds=True, eds_clamp=400.0, want_msp=True,
+                              want_minmax=True, gt=gt, confusion=conf, out=o)
+
+    ms = _timed_ms(torch, fused, 10)
+    out["config1_multiscale_head_50x5scales_720x1280"] = entry(B * size[0] * size[1], 10, ms, kernel="head_kernel<13,MSS,2,false> (+5 stride-8 heads)",
+                                                              note="FP32-pipe bound (65 bilinear blends per pixel), not HBM bound")
+    return out
+
+
+def verify_pooled(pipe, world, rank, images=4):
+    """Driver-visible correctness of the pooled metric: the packed keys of the first `images` images of every rank are
+    (a) evaluated by the path the timed step uses (single GPU: KeyPool / rank_keys; N > 1: the NCCL exchange) and
+    (b) gathered on rank 0 and evaluated there as ONE segment by the single-GPU radix-sort path.  AUROC / FPR must be
+    bit-equal (integer counting), AUPR equal to float64 summation order (1e-12)."""
+    import torch
+    import torch.distributed as dist
+    from dml_b200 import ood, distributed as D
+    if pipe.pool is None:
+        return None
+    m = min(images, pipe.n)
+    nk = m * pipe.hw
+    keys = pipe.pool.keys[:nk].clone()
+    st = pipe.per_image_stats[:m].sum(0)
+    st[3] = 0
+    rank_mode = pipe.args.metric_method == "rank"
+    if world == 1 and not rank_mode:
+        return {"verified": None, "note": "single GPU sort path is the reference itself"}
+    ws = ood.OodWorkspace(pipe.device)
+    if world == 1:
+        if rank_mode:
+            got = ood.rank_keys(keys, st.view(1, 4), recall_level=0.95, workspace=ws).cpu().numpy()[0, :3]
+        else:
+            got = None
+        all_keys, tot = keys, st
+    else:
+        a, p_, f, _ = D.pooled_measures(None, None, (pipe.k,), workspace=ws, keys_and_stats=(keys, st),
+                                        mode="rank" if rank_mode else "partition")
+        got = np.array([a, p_, f])
+        gathered = [torch.empty_like(keys) for _ in range(world)] if rank == 0 else None
+        dist.gather(keys, gathered, dst=0)
+        tot = st.clone()
+        dist.all_reduce(tot)
+        all_keys = torch.cat(gathered) if rank == 0 else None
+    if rank != 0:
+        return None
+    n_all = all_keys.numel()
+    res = torch.empty(1, 7, dtype=torch.float64, device=pipe.device)
+    scratch = torch.empty(pipe.lib.dml_ood_workspace_bytes(1, n_all), dtype=torch.uint8, device=pipe.device)
+    from dml_b200._lib import check, ptr, stream_ptr
+    work = all_keys.clone()
+    check(pipe.lib.dml_ood_eval_segments(ptr(work), ptr(tot.view(1, 4).contiguous()), 1, n_all, 0.95, ptr(scratch), scratch.numel(), 0,
+                                         ptr(res), stream_ptr(pipe.device)), "dml_ood_eval_segments")
+    ref = res.cpu().numpy()[0, :3]
+    if got is None:
+        return {"verified": None, "note": "single GPU sort path is the reference itself"}
+    ok = bool(got[0] == ref[0] and got[2] == ref[2] and abs(got[1] - ref[1]) <= 1e-12)
+    return {"verified": ok, "pairs": int(n_all), "images_per_rank": m, "d_auroc": float(got[0] - ref[0]),
+            "d_aupr": float(got[1] - ref[1]), "d_fpr": float(got[2] - ref[2]),
+            "reference": "all ranks' keys gathered on rank 0, one segment, single-GPU radix sort + scan"}
+
+
+def strong_scaling_run(args, device, rank, world, x_all, gt_all, barrier, total_images, steps=2):
+    """Fixed TOTAL work sharded over the ranks (the north star's "1500 x 720 x 1280 ... scales near-linearly to 8 GPUs"):
+    every rank runs the full step on total_images / world of its resident images; max over ranks."""
+    import copy
+    import torch
+    import torch.distributed as dist
+    a2 = copy.copy(args)
+    a2.images = max(1, total_images // world)
+    pipe = Pipeline(a2, device, rank, world)
+    xs, gs = x_all[:a2.images], gt_all[:a2.images]
+    pipe.step_resident(xs, gs)
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(steps):
+        pipe.step_resident(xs, gs)
+    ev1.record()
+    barrier()
+    t = torch.tensor([ev0.elapsed_time(ev1) / steps], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    out = {"images_total": a2.images * world, "images_per_gpu": a2.images, "steps": steps, "ms_per_step": ms,
+           "value": a2.images * world * pipe.hw / (ms * 1e-3) / 1e6, "unit": UNIT}
+    if world > 1 and pipe.pooled_result is not None:
+        out["pooled_phases_ms_rank0"] = {k: round(v, 3) for k, v in pipe.pooled_result[3].get("phase_ms", {}).items()}
+    del pipe
+    torch.cuda.empty_cache()
+    return out
+
+
+def config5_run(args, device, rank, world, barrier, total_images, steps=2):
+    """BASELINE.json configs[4]: the exact pooled metric over `total_images` synthetic images sharded over the ranks
+    (sorted shards of the positives merged through an NCCL all-gather, mode="rank"; or the key-range exchange,
+    mode="partition").  The (conf, gt) keys are produced chunk by chunk by the head + per-image pass on freshly
+    generated embeddings (untimed); the timed region is the pooled metric stage alone, max over ranks."""
+    import torch
+    import torch.distributed as dist
+    from dml_b200 import head as H, ood, distributed as D
+    k, h, w = args.classes, args.height, args.width
+    hw = h * w
+    m = max(1, total_images // world)
+    ws = ood.OodWorkspace(device)
+    pool = ood.KeyPool(m * hw, device, workspace=ood.OodWorkspace(device), histograms=False)
+    gen = torch.Generator(device=device).manual_seed(5000 + rank)
+    chunk = 37
+    method = args.metric_method
+    for s0 in range(0, m, chunk):
+        nb = min(chunk, m - s0)
+        x, gt = synth_chunk_torch(nb, k, h, w, gen, device)
+        o = H.dml_head(x, magnitude=3.0, want_logits=False, label_dtype=torch.uint8, want_eds=True, eds_clamp=400.0,
+                       want_minmax=True)
+        ood.eval_segments(o.eds, nb, hw, gt=gt, out_labels=(k,), minmax=o.minmax, workspace=ws, pool=pool, method=method)
+        del x, gt, o
+    mode = "rank" if method == "rank" else "partition"
+    wsp = ood.OodWorkspace(device)
+
+    def run():
+        if world == 1:
+            return pool.evaluate(method="rank" if method == "rank" else "sort")
+        ks = (pool.keys, pool.stats[0])
+        if mode == "rank" and pool.pos is not None:
+            ks = ks + (pool.pos, pool.pos_count)
+        return D.pooled_measures(None, None, (k,), workspace=wsp, keys_and_stats=ks, mode=mode, timing=True)
+
+    run()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(steps):
+        r = run()
+    ev1.record()
+    barrier()
+    t = torch.tensor([ev0.elapsed_time(ev1) / steps], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    out = {"images_total": m * world, "images_per_gpu": m, "pairs_total": m * world * hw, "mode": mode, "steps": steps,
+           "pooled_metric_ms": ms, "Gpairs_per_s": m * world * hw / (ms * 1e-3) / 1e9}
+    if world > 1:
+        out["pooled"] = {"auroc": r[0], "aupr": r[1], "fpr95": r[2]}
+        out["phases_ms_rank0"] = {kk: round(v, 3) for kk, v in r[3].get("phase_ms", {}).items()}
+        out["exchanged_bytes_rank0"] = r[3].get("exchanged_bytes")
+    del pool, ws, wsp
+    torch.cuda.empty_cache()
+    return out
 
 def bind_to_gpu_numa_node(index):
     """Pin this process to the CPUs NVML reports as local to GPU `index`, BEFORE any pinned host buffer is allocated,
@@ -371,6 +687,49 @@ def bind_to_gpu_numa_node(index):
     except Exception:
         pass
     return None
+
+
+MPOL_DEFAULT, MPOL_BIND = 0, 2
+SYS_SET_MEMPOLICY = 238          # x86-64
+
+
+def gpu_numa_node(index):
+    """NUMA node of GPU `index` from the PCI sysfs entry (NVML's CPU affinity is clipped to the container's cpuset and
+    showed 0-31 for all eight GPUs in round 1; the PCI device knows its real node).  None when it cannot be read."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(index)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        dom, rest = bus.split(":", 1)
+        path = f"/sys/bus/pci/devices/{dom[-4:].lower()}:{rest.lower()}/numa_node"
+        node = int(open(path).read().strip())
+        return node if node >= 0 else None
+    except Exception:
+        return None
+
+
+def set_mempolicy(mode, node=None):
+    """set_mempolicy(2) through libc's syscall(): MPOL_BIND to `node` makes every page this process touches next
+    (the pinned staging ring) come from that node no matter which CPU runs the thread; MPOL_DEFAULT restores
+    first-touch.  Returns True on success; any failure (no permission in the container, one node) is harmless."""
+    try:
+        import ctypes
+        libc = ctypes.CDLL(None, use_errno=True)
+        if mode == MPOL_DEFAULT:
+            return libc.syscall(SYS_SET_MEMPOLICY, MPOL_DEFAULT, None, 0) == 0
+        mask = ctypes.c_ulong(1 << int(node))
+        return libc.syscall(SYS_SET_MEMPOLICY, mode, ctypes.byref(mask), 64) == 0
+    except Exception:
+        return False
+
+
+def host_topology():
+    try:
+        nodes = open("/sys/devices/system/node/online").read().strip()
+    except Exception:
+        nodes = None
+    return {"numa_nodes_online": nodes, "cpus_in_cpuset": len(os.sched_getaffinity(0)), "cpu_count": os.cpu_count()}
 
 
 def run_ours(args):
@@ -477,15 +836,23 @@ def run_ours(args):
     pool_ms = [a.elapsed_time(b) for a, b in pipe.pooled_events]
     stages = [{"stage": "head (dominant streaming kernel, roofline above)", "ms_per_step": sum(head_ms) / args.steps,
                "share_of_step": sum(head_ms) / ms_total}]
+    rank_mode = args.metric_method == "rank"
     if met_ms:
-        gbs = tot_px * 69 / (sum(met_ms) * 1e-3) / 1e9
-        stages.append({"stage": "per-image exact metrics: key-gen + segmented radix sort (4 x 8 bit) + tie-aware scan",
+        # rank method: gt 1 (positives gather) + eds 4 + msp 4 + gt 1 read, conf 4 + mmsp 4 + mix 4 + pooled key 4 written
+        met_bpp = (26 if pipe.pool is not None else 22) if rank_mode else 69
+        gbs = tot_px * met_bpp / (sum(met_ms) * 1e-3) / 1e9
+        stages.append({"stage": ("per-image exact metrics, minority-rank path: positives gathered + sorted in shared memory, every "
+                                 "negative located among them in the pass that writes the conf / MMSP / mix maps, group scan"
+                                 if rank_mode else
+                                 "per-image exact metrics: key-gen + segmented radix sort (4 x 8 bit) + tie-aware scan"),
                        "ms_per_step": sum(met_ms) / args.steps, "share_of_step": sum(met_ms) / ms_total,
-                       "bytes_per_pair_model": 69, "achieved_GBps": gbs, "frac_of_hbm_peak": gbs / peak,
+                       "bytes_per_pair_model": met_bpp, "achieved_GBps": gbs, "frac_of_hbm_peak": gbs / peak,
                        "Gpairs_per_s": tot_px / (sum(met_ms) * 1e-3) / 1e9})
-    pool_bpp = 40 if pipe.pool is not None else 53
+    # pooled: sort = 4 x 8 (+ 4 counting read if no histograms) + scan 8; rank = compact 4 + count 4 + scatter 8 + locate 4
+    pool_bpp = 20 if rank_mode else (40 if pipe.pool is not None else 53)
     if pool_ms and not args.no_pooled:
-        stages.append({"stage": "pooled exact metrics over all pairs of the step" + (" (local part + NCCL exchange)" if world > 1 else ""),
+        stages.append({"stage": "pooled exact metrics over all pairs of the step" + (" (local part + NCCL exchange)" if world > 1 else "") +
+                                (": positives sorted, negatives bucketed + located (no sort of the negatives)" if rank_mode else ": radix sort + scan"),
                        "ms_per_step": sum(pool_ms) / args.steps, "share_of_step": sum(pool_ms) / ms_total,
                        "bytes_per_pair_model": pool_bpp if world == 1 else None,
                        "achieved_GBps": (tot_px * pool_bpp / (sum(pool_ms) * 1e-3) / 1e9) if world == 1 else None,
@@ -494,7 +861,9 @@ def run_ours(args):
             info = pipe.pooled_result[3]
             stages[-1]["phases_ms_last_step_rank0"] = {k: round(v, 3) for k, v in info.get("phase_ms", {}).items()}
             stages[-1]["exchanged_bytes_rank0"] = info.get("exchanged_bytes")
+    stages.sort(key=lambda st: -st["share_of_step"])        # largest share of the step first
     roofline["stages"] = stages
+    roofline["traffic_source"] = "profiles/head_traffic.json (ncu dram__bytes of head_kernel, r1d capture; not re-measured in this run)"
 
     # ---- results (also the parity self-check of the bench) ------------------------------------------
     vals, counts = pipe.ood.results_to_host(pipe.per_image, pipe.per_image_stats)
@@ -509,6 +878,23 @@ def run_ours(args):
             a, p_, f = pipe.pooled_result[:3]
             summary.update({"pooled_auroc": float(a), "pooled_aupr": float(p_), "pooled_fpr95": float(f)})
 
+    if world > 1 and pipe.mean_all_ranks is not None:
+        ma = pipe.mean_all_ranks
+        summary.update({"all_ranks_mean_auroc": ma[0], "all_ranks_mean_aupr": ma[1], "all_ranks_mean_fpr95": ma[2],
+                        "all_ranks_images_scored": ma[3], "all_ranks_confusion_total": int(pipe.confusion_all.sum().item())})
+
+    # ---- bounded side measurements: pooled self-check, the other configs' kernels, strong scaling, config 5 --------
+    pooled_check = extra = strong = config5 = None
+    if not args.no_extra:
+        if not args.no_pooled:
+            pooled_check = verify_pooled(pipe, world, rank)
+        if rank == 0 and world == 1:
+            extra = extra_rooflines(device, peak)
+        if world > 1:
+            strong = strong_scaling_run(args, device, rank, world, x_all, gt_all, barrier, n)
+            if args.config5_images and not args.no_pooled:
+                config5 = config5_run(args, device, rank, world, barrier, args.config5_images)
+
     # ---- end-to-end: host pinned ring -> H2D -> step -> D2H -------------------------------------------
     e2e = None
     if not args.no_e2e:
@@ -516,6 +902,13 @@ def run_ours(args):
         if world > 1:
             t = torch.tensor([e2e["ms_per_step"]], dtype=torch.float64, device=device)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            # per-rank H2D rates and NUMA placement of every rank (rank 0 prints them)
+            mine = torch.tensor([e2e["h2d_GBps_this_rank"], -1.0 if e2e["gpu_numa_node"] is None else float(e2e["gpu_numa_node"]),
+                                 1.0 if e2e["ring_bound_to_gpu_node"] else 0.0], dtype=torch.float64, device=device)
+            allr = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(allr, mine)
+            allr = torch.stack(allr).cpu().tolist()
+            e2e["per_rank"] = [{"h2d_GBps": round(r[0], 2), "gpu_numa_node": int(r[1]), "ring_bound": bool(r[2])} for r in allr]
             e2e["ms_per_step"] = float(t.item())
         e2e["value"] = world * n * hw / (e2e["ms_per_step"] * 1e-3) / 1e6
 
@@ -539,15 +932,30 @@ def run_ours(args):
                 "data": "synthetic",
                 "config": {"workload": workload_name(args), "images_per_gpu": n, "chunk_images": pipe.chunk,
                            "l2": "inputs (%.1f GB/step/GPU) far exceed the 126 MB L2; no flush needed" % (n * k * hw * 4 / 1e9),
-                           "pooled": ("single GPU sort" if world == 1 else
-                                      "range partition of the unsorted keys + NCCL all-to-all + one local sort per rank (mode=partition)") +
-                                     ("; keys" + (" and digit histograms" if world == 1 else "") + " reused from the per-image pass"
+                           "metric_method": args.metric_method,
+                           "pooled": (("minority rank: positives compacted + sorted, negatives bucketed and located among them" if world == 1 else
+                                       "minority rank: locally sorted positive shards merged through an NCCL all-gather, every rank locates "
+                                       "its own negatives, counters all-reduced (mode=rank)") if rank_mode else
+                                      ("single GPU sort" if world == 1 else
+                                       "range partition of the unsorted keys + NCCL all-to-all + one local sort per rank (mode=partition)")) +
+                                     ("; keys" + (" and digit histograms" if world == 1 and not rank_mode else "") + " reused from the per-image pass"
                                       if pipe.pool is not None else "; keys regenerated from the conf maps")},
                 "roofline": roofline, "cpu_baseline": cpu,
                 "e2e": ({"value": e2e["value"], "unit": UNIT, "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
                          "ms_per_step": e2e["ms_per_step"], "steps": e2e["steps"], "note": e2e["note"],
-                         "cpus_bound_to_gpu_numa_node": numa_cpus} if e2e else None),
+                         "cpus_bound_to_gpu_numa_node": numa_cpus, "h2d_GBps_rank0": e2e["h2d_GBps_this_rank"],
+                         "gpu_numa_node": e2e["gpu_numa_node"], "ring_bound_to_gpu_node": e2e["ring_bound_to_gpu_node"],
+                         "per_rank": e2e.get("per_rank"), "host": host_topology()} if e2e else None),
                 "gpu_launches": int(launches), "clocks": clocks, "results": summary}
+        if pooled_check is not None:
+            line["pooled_verified"] = pooled_check.get("verified")
+            line["pooled_verify"] = pooled_check
+        if extra is not None:
+            roofline["extra"] = extra
+        if strong is not None:
+            line["strong_scaling"] = strong
+        if config5 is not None:
+            line["config5_metric_sweep"] = config5
         emit_json_line(line)
     if world > 1:
         dist.destroy_process_group()
@@ -561,6 +969,10 @@ def run_e2e(args, pipe, x_all, gt_all, device, world, barrier):
     n, k, h, w = pipe.n, pipe.k, pipe.h, pipe.w
     ring_n = min(4, len(pipe.bounds))
     ring_x, ring_g = [], []
+    # the staging ring lives on the GPU's own NUMA node (8 ranks otherwise share one node's memory controllers and
+    # half of them DMA across the socket interconnect)
+    node = gpu_numa_node(device.index if device.index is not None else 0)
+    bound = set_mempolicy(MPOL_BIND, node) if node is not None else False
     for i in range(ring_n):
         s, e = pipe.bounds[i]
         hx = torch.empty(e - s, k, h, w, dtype=torch.float32).pin_memory()
@@ -569,6 +981,8 @@ def run_e2e(args, pipe, x_all, gt_all, device, world, barrier):
         hg.copy_(gt_all[s:e])
         ring_x.append(hx)
         ring_g.append(hg)
+    if bound:
+        set_mempolicy(MPOL_DEFAULT)
     torch.cuda.synchronize()
     c = pipe.chunk
     stage_x = [torch.empty(c, k, h, w, dtype=torch.float32, device=device) for _ in range(2)]
@@ -619,6 +1033,7 @@ def run_e2e(args, pipe, x_all, gt_all, device, world, barrier):
     barrier()
     ms = ev0.elapsed_time(ev1) / max(args.e2e_steps, 1)
     return {"ms_per_step": ms, "h2d": int(h2d), "d2h": int(d2h), "steps": args.e2e_steps,
+            "h2d_GBps_this_rank": h2d / (ms * 1e-3) / 1e9, "gpu_numa_node": node, "ring_bound_to_gpu_node": bool(bound),
             "note": f"inputs in pinned host memory (ring of {ring_n} distinct {c}-image chunks), H2D double-buffered "
                     f"on a copy stream; results (per-image metrics, confusion, pooled) copied D2H"}
 

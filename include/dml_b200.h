@@ -188,6 +188,16 @@ DML_API int dml_plm_merge(uint8_t* base_u8, int64_t* base_i64, const uint8_t* he
                   int64_t n, int32_t novel_label, dml_stream_t stream);
 
 /* ------------------------------------------------------------------------------------ *
+ * (f-2) Final 1x1 classifier conv fused into the distance head (inference).
+ *   anomaly/models/models.py:609 (conv_last[4] = nn.Conv2d(512, num_class, 1)) + :636-657 (distance block)
+ *   DeepLabV3Plus-Pytorch/network/utils.py:23 (classifier[3] = nn.Conv2d(256, num_classes, 1))
+ * features [B,C,H,W] (the post-ReLU output of the layer before), weight [K,C] (the conv's [K,C,1,1] weight), bias [K]
+ * or NULL.  embedding[b,k,p] = sum_c weight[k,c] features[b,c,p] + bias[k] (fp32 FFMA, channel order);
+ * logits[b,k,p] = -sum_d (embedding_d - diag_m [d = k])^2.  Either output may be NULL.  K <= 32. */
+DML_API int dml_conv1x1_head_forward(const float* features, const float* weight, const float* bias, float diag_m, int32_t B,
+                             int32_t C, int32_t K, int32_t H, int32_t W, float* embedding, float* logits, dml_stream_t stream);
+
+/* ------------------------------------------------------------------------------------ *
  * (b) Fused DCE + VL (+ Inter) loss, forward and backward, straight from the embedding.
  *   anomaly/models/models.py:42-78 (CE + alpha*VL, ignore -1)
  *   DeepLabV3Plus-Pytorch/utils/loss.py:34-82 (line 79 form; shipped early return = alpha=beta=0)
@@ -344,6 +354,42 @@ DML_API int dml_ood_rank_segments(const float* values, const float* minmax, int3
                           long long* seg_stats, const float* msp, float* msp_norm_out, float* mix_out, float lambda,
                           float thr, int32_t pos_capacity, double recall_level, void* workspace, size_t workspace_bytes,
                           dml_ood_result* results, dml_stream_t stream);
+
+/* Appends the positives' score keys (key >> 1) of every segment of the LAST dml_ood_rank_segments call on
+ * `rank_workspace` (same n_seg / pos_capacity) to `out` at *count (device, running total, in/out): a pooled evaluation
+ * over many batches then needs no pass over all keys to find its positives.  Segments flagged as overflowed export
+ * nothing (the caller notices *count < the pooled n_pos and falls back to dml_ood_pos_compact). */
+DML_API int dml_ood_rank_export_positives(const void* rank_workspace, size_t workspace_bytes, int32_t n_seg, int32_t pos_capacity,
+                                  uint32_t* out, int64_t out_capacity, long long* count, dml_stream_t stream);
+
+/* ------------------------------------------------------------------------------------ *
+ * (d'') Pooled metric on the minority-rank idea: building blocks for ONE ranking of up to 2^32 - 1 pairs (the
+ * full-set AUROC / AUPR / FPR@95 of the north star; reference semantics anomaly/anom_utils.py:25-78 over all pixels)
+ * whose negatives are never sorted and -- across GPUs -- never exchanged:
+ *   dml_ood_pos_compact    packed keys (bit 0 = positive) -> score keys (key >> 1) of the positives, any order;
+ *                          *count (device) = number of positives (may exceed `capacity`: then only `capacity` were kept)
+ *   dml_ood_sort           sort them (bits [0, 31))
+ *   dml_ood_unique_counts  sorted score keys -> distinct values + multiplicities, *n_unique (device)
+ *   dml_ood_bucket_rank    counters (device, 2 * n_groups + 2 uint64, zeroed by the call):
+ *                          [2g] = negatives strictly between group g-1 and g, [2g + 1] = negatives tied with group g,
+ *                          [2 * n_groups] = negatives above every positive.  Negatives are grouped into buckets of
+ *                          <= 12288 consecutive positive groups by one counting + one non-stable scatter pass, then
+ *                          located in shared memory.  DML_ERR_UNSUPPORTED_DIM: more than 4096 * 12288 distinct positive
+ *                          scores (use the sort path).  Counters of several key sets (ranks) simply add.
+ *   dml_ood_pooled_scan    scan over the groups -> *result (device); n_groups == 0 / one class empty -> NaN.
+ * The host reads *count and *n_unique between the calls (two small synchronisations per pooled evaluation). */
+DML_API int dml_ood_pos_compact(const uint32_t* keys, int64_t n, uint32_t* pos_keys_out, int64_t capacity, long long* count,
+                        dml_stream_t stream);
+DML_API size_t dml_ood_unique_workspace_bytes(int64_t n);
+DML_API int dml_ood_unique_counts(const uint32_t* sorted_keys, int64_t n, uint32_t* values_out, uint32_t* counts_out,
+                          long long* n_unique, void* workspace, size_t workspace_bytes, dml_stream_t stream);
+DML_API size_t dml_ood_bucket_rank_workspace_bytes(int64_t n, int64_t n_groups);
+DML_API int dml_ood_bucket_rank(const uint32_t* keys, int64_t n, const uint32_t* group_scores, int64_t n_groups, uint32_t key_base,
+                        unsigned long long* counters, void* workspace, size_t workspace_bytes, dml_stream_t stream);
+DML_API size_t dml_ood_pooled_scan_workspace_bytes(int64_t n_groups);
+DML_API int dml_ood_pooled_scan(const uint32_t* group_counts, const unsigned long long* counters, int64_t n_groups,
+                        int64_t total_pos, int64_t total_n, int64_t n_nan, double recall_level, void* workspace,
+                        size_t workspace_bytes, dml_ood_result* result, dml_stream_t stream);
 
 /* "partition" exchange mode of the multi-GPU pooled metric: scatter UNSORTED packed keys into n_buckets
  * contiguous key ranges (one per rank), ship range r to rank r, sort only what is received -- one partition

@@ -75,6 +75,8 @@ SIGNATURES = {
     "dml_kernel_launches": (C.c_ulonglong, []),
     "dml_head_forward": (C.c_int, [C.POINTER(HeadParams), C.c_void_p]),
     "dml_multiscale_head_forward": (C.c_int, [C.POINTER(MultiscaleParams), C.c_void_p]),
+    "dml_conv1x1_head_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                           C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "dml_scores_finalize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_float,
                                       C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "dml_confusion": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32,
@@ -114,6 +116,18 @@ SIGNATURES = {
                                         C.c_void_p, C.c_int32, C.c_uint32, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_int32, C.c_double,
                                         C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
+    "dml_ood_rank_export_positives": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p,
+                                                C.c_void_p]),
+    "dml_ood_pos_compact": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "dml_ood_unique_workspace_bytes": (C.c_size_t, [C.c_int64]),
+    "dml_ood_unique_counts": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
+                                        C.c_void_p]),
+    "dml_ood_bucket_rank_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int64]),
+    "dml_ood_bucket_rank": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_uint32, C.c_void_p, C.c_void_p,
+                                      C.c_size_t, C.c_void_p]),
+    "dml_ood_pooled_scan_workspace_bytes": (C.c_size_t, [C.c_int64]),
+    "dml_ood_pooled_scan": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_double,
+                                      C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
     "dml_ood_scan_range": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_double, C.c_void_p, C.c_size_t,
                                      C.c_void_p, C.c_void_p]),
 }

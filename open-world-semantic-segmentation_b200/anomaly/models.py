@@ -8,6 +8,7 @@ from __future__ import annotations
 import torch
 import torch.nn as nn
 
+from .. import head as H
 from ..autograd import distance_logits
 
 BatchNorm2d = nn.BatchNorm2d  # the reference aliases its vendored SynchronizedBatchNorm2d (same state_dict keys)
@@ -51,6 +52,12 @@ class PPMDeepsup_embedding(nn.Module):
         size = conv5.shape[2:]
         ppm_out = torch.cat([conv5] + [nn.functional.interpolate(p(conv5), size, mode='bilinear', align_corners=False)
                                        for p in self.ppm], 1)
+        if not torch.is_grad_enabled() and ppm_out.is_cuda and ppm_out.dtype == torch.float32 and not self.training:
+            # inference: the final 1x1 conv (:609) is fused into the distance head -- the 512-channel
+            # feature is read once, embedding and logits leave the same kernel
+            feat = self.conv_last[:4](ppm_out)
+            emb, z = H.conv1x1_head(feat, self.conv_last[4].weight, self.conv_last[4].bias, self.magnitude)
+            return z, emb
         emb = self.conv_last(ppm_out)
         return distance_logits(emb, magnitude=self.magnitude), emb
 

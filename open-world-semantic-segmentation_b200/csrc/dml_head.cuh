@@ -729,11 +729,28 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_kernel(const HeadArgs a) {
       st_keep<VEC>(a.msp + pix, t);
     }
     if constexpr (EXTRA) if (om & OUT_FEAT) {
+      // NHWC copy: the D channels of a pixel are contiguous -- 16-byte stores when the row length allows it
+      // (cudaMalloc'ed / torch tensors are 256-byte aligned; D % 4 == 0 keeps every pixel 16-byte aligned)
       float* f = a.feat + pix * D;
+      if constexpr (D % 4 == 0) {
+        if ((reinterpret_cast<uintptr_t>(a.feat) & 15) == 0) {
 #pragma unroll
-      for (int v = 0; v < VEC; ++v)
+          for (int v = 0; v < VEC; ++v)
 #pragma unroll
-        for (int d = 0; d < D; ++d) f[v * D + d] = x[d][v];
+            for (int d = 0; d < D; d += 4)
+              *reinterpret_cast<float4*>(f + v * D + d) = make_float4(x[d][v], x[d + 1][v], x[d + 2][v], x[d + 3][v]);
+        } else {
+#pragma unroll
+          for (int v = 0; v < VEC; ++v)
+#pragma unroll
+            for (int d = 0; d < D; ++d) f[v * D + d] = x[d][v];
+        }
+      } else {
+#pragma unroll
+        for (int v = 0; v < VEC; ++v)
+#pragma unroll
+          for (int d = 0; d < D; ++d) f[v * D + d] = x[d][v];
+      }
     }
   }
 

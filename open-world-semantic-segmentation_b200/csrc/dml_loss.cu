@@ -79,7 +79,9 @@ int loss_common(bool bwd, bool is_logits, const float* x, const float* mu, float
   if (bwd ? (!grad_out || !dx) : !partials) return DML_ERR_INVALID_ARG;
   const long long hw = (long long)H * W;
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
-  int vec = (ident && hw % 4 == 0 && al16(x) && (!bwd || al16(dx))) ? 4 : 1;
+  // (vector target loads: uint8 targets 4-byte aligned, int64 targets 16-byte aligned)
+  const bool t_al = t_u8 ? (reinterpret_cast<uintptr_t>(t_u8) & 3) == 0 : al16(t_i64);
+  int vec = (ident && hw % 4 == 0 && al16(x) && t_al && (!bwd || al16(dx))) ? 4 : 1;
   if (D > 24) vec = 1;
   LossArgs a;
   a.x = x; a.mu = mu; a.diag_m = diag_m; a.t_u8 = t_u8; a.t_i64 = (const long long*)t_i64; a.ignore = ignore_index;

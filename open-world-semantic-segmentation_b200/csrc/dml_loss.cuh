@@ -82,9 +82,25 @@ __global__ void __launch_bounds__(LOSS_THREADS) loss_kernel(const LossArgs a) {
       for (int v = 0; v < VEC; ++v) x[d][v] = t.v[v];
     }
     const long long pix = (long long)b * a.HW + p0;
+    // the VEC targets of the thread in one or two vector loads (VEC == 4: p0 and H*W are multiples of 4)
+    long long tg[VEC];
+    if constexpr (VEC == 4) {
+      if (a.t_u8) {
+        const uchar4 t = *reinterpret_cast<const uchar4*>(a.t_u8 + pix);
+        tg[0] = t.x; tg[1] = t.y; tg[2] = t.z; tg[3] = t.w;
+      } else {
+        const longlong2 t0 = *reinterpret_cast<const longlong2*>(a.t_i64 + pix);
+        const longlong2 t1 = *reinterpret_cast<const longlong2*>(a.t_i64 + pix + 2);
+        tg[0] = t0.x; tg[1] = t0.y; tg[2] = t1.x; tg[3] = t1.y;
+      }
+    } else {
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) tg[v] = a.t_u8 ? (long long)a.t_u8[pix + v] : a.t_i64[pix + v];
+    }
+    float ce_f = 0.f, vl_f = 0.f, in_f = 0.f;   // the thread's VEC pixels are pre-added in fp32, one fp64 add per iteration
 #pragma unroll
     for (int v = 0; v < VEC; ++v) {
-      const long long tgt = a.t_u8 ? (long long)a.t_u8[pix + v] : a.t_i64[pix + v];
+      const long long tgt = tg[v];
       const bool valid = (tgt != a.ignore) && tgt >= 0 && tgt < K;
       const int y = valid ? (int)tgt : 0;
 
@@ -162,9 +178,9 @@ __global__ void __launch_bounds__(LOSS_THREADS) loss_kernel(const LossArgs a) {
             dsum = (float)D * sumsq - two_m * sx + (float)D * a.diag_m * a.diag_m;
           }
           const float ce = log1pf(r) - uy;  // logsumexp_k z_k - z_y
-          ce_acc += (double)ce;
-          vl_acc += (double)dy;
-          in_acc += (double)(-(dsum - dy));
+          ce_f += ce;
+          vl_f += dy;
+          in_f += -(dsum - dy);
           ++nv_acc;
         }
       } else {
@@ -198,6 +214,11 @@ __global__ void __launch_bounds__(LOSS_THREADS) loss_kernel(const LossArgs a) {
           for (int d = 0; d < D; ++d) x[d][v] = valid ? -2.0f * gx[d] : 0.f;
         }
       }
+    }
+    if constexpr (!BWD) {
+      ce_acc += (double)ce_f;
+      vl_acc += (double)vl_f;
+      in_acc += (double)in_f;
     }
     if constexpr (BWD) {
       float* db = a.dx + ((long long)b * D) * a.HW + p0;

@@ -18,15 +18,15 @@
 // sort path and AUPR differs by float64 summation order only.  Segments whose positives exceed `pos_capacity` are flagged
 // (seg_stats[seg][3] = 1, NaN result): the caller re-evaluates those with the sort path (dml_ood_keygen +
 // dml_ood_eval_segments), which has no such limit.
-#include "ood_sort.cuh"
-#include "ood_scan_thread.cuh"
+#include "ood_rank.cuh"
 
 namespace dml {
 namespace {
 
-constexpr int RANK_THREADS = 1024;
-constexpr int RANK_LUT = 8192;          // value-linear index table over [f(S[first]), f(S[last])] of a pass
-constexpr int RANK_SORT_MAX = 32768;    // positives per segment the shared-memory bitonic sort handles (128 KB)
+constexpr int RANK_SORT_MAX = 32768;    // positives per segment the shared-memory sort handles (128 KB)
+constexpr int BUCKET_SORT_MAX = 16384;  // ... of which the bucket sort handles this many (else: bitonic network)
+constexpr int BUCKET_SORT_NB = 8192;    // value-linear buckets
+constexpr int BUCKET_SORT_RUN = 48;     // largest bucket the per-bucket insertion sort accepts (else: bitonic network)
 
 struct RankWs {  // carve-up of the workspace (byte offsets); per segment `cap` entries
   size_t off_plist, off_S, off_pc, off_cnt, off_G, off_cursor, off_end;
@@ -43,29 +43,6 @@ RankWs make_rank_ws(int n_seg, int cap) {
   w.off_cursor = align(w.off_G + (size_t)n_seg * sizeof(uint32_t));
   w.off_end = align(w.off_cursor + (size_t)n_seg * sizeof(uint32_t));
   return w;
-}
-
-// float whose order is the key order (inverse of pack_key's sortable image): kind 0 -> conf, kind 1 -> -score
-__device__ __forceinline__ float key_float(uint32_t skey, uint32_t key_base) {
-  const uint32_t srt = skey + key_base;
-  const uint32_t u = (srt & 0x80000000u) ? (srt ^ 0x80000000u) : ~srt;
-  return __uint_as_float(u);
-}
-
-// per-segment normalisation constants, as dml_ood_keygen applies them
-struct Norm { float lo, den; bool on; };
-__device__ __forceinline__ Norm load_norm(const float* __restrict__ minmax, int seg, int slot) {
-  Norm n;
-  n.on = minmax != nullptr;
-  n.lo = 0.f; n.den = 1.f;
-  if (n.on) {
-    n.lo = minmax[seg * 4 + slot * 2];
-    n.den = __fsub_rn(minmax[seg * 4 + slot * 2 + 1], n.lo);
-  }
-  return n;
-}
-__device__ __forceinline__ float apply_norm(const Norm& n, float v) {
-  return n.on ? __fdiv_rn(__fsub_rn(v, n.lo), n.den) : v;   // NumPy: (x - min) / (max - min), fp32
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -97,11 +74,7 @@ __global__ void __launch_bounds__(256) pos_gather_kernel(const float* __restrict
         const uint4 w = *reinterpret_cast<const uint4*>(gb + base + p0);
         const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
-        for (int j = 0; j < PER; ++j) {
-          const unsigned g = (ww[j >> 2] >> (8 * (j & 3))) & 255u;
-          const bool pos = pos_u8 ? (g != 0) : (g < 64 && ((out_mask >> g) & 1ull));
-          flags |= (pos ? 1u : 0u) << j;
-        }
+        for (int j = 0; j < 4; ++j) flags |= byte_mask_to_bits(positive_bytes(ww[j], out_mask, pos_u8 != nullptr)) << (4 * j);
       } else {
         for (int j = 0; j < PER; ++j) {
           const long long p = p0 + j;
@@ -130,28 +103,38 @@ __global__ void __launch_bounds__(256) pos_gather_kernel(const float* __restrict
     if (lane == 31) wbase = atomicAdd(cursor + seg, (uint32_t)total);
     wbase = __shfl_sync(0xffffffffu, wbase, 31);
     uint32_t dst = wbase + (uint32_t)(incl - c);
-    while (flags) {
-      const int j = __ffs(flags) - 1;
-      flags &= flags - 1u;
-      if (dst < (uint32_t)cap) {
-        const float v = apply_norm(nm, values[base + p0 + j]);
-        unsigned d0 = 0, d1 = 0;
-        out[dst] = pack_key(v, kind, true, key_base, d0, d1) >> 1;
+    // all of the thread's (sparse) value loads are issued before the first one is consumed: one memory latency per
+    // step instead of one per positive
+    float vv[PER];
+#pragma unroll
+    for (int j = 0; j < PER; ++j) vv[j] = ((flags >> j) & 1u) ? values[base + p0 + j] : 0.f;
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+      if ((flags >> j) & 1u) {
+        if (dst < (uint32_t)cap) {
+          unsigned d0 = 0, d1 = 0;
+          out[dst] = pack_key(apply_norm(nm, vv[j]), kind, true, key_base, d0, d1) >> 1;
+        }
+        ++dst;
       }
-      ++dst;
     }
   }
 }
 
 // ---------------------------------------------------------------------------------------------
-// 2. per segment: bitonic sort in shared memory, distinct scores S[g] + multiplicities pc[g], zeroed counters
+// 2. per segment: sort in shared memory, distinct scores S[g] + multiplicities pc[g], zeroed counters.
+//    Usual case (<= BUCKET_SORT_MAX positives, no long run of equal scores): bucket sort over BUCKET_SORT_NB
+//    value-linear buckets (LinIndex is monotone, so bucket order == key order) -- two coalesced reads of the list,
+//    one shared atomic per key, then every bucket (a handful of keys) is insertion-sorted by one thread.
+//    Otherwise: bitonic network over the padded list.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(RANK_THREADS) pos_sort_kernel(const uint32_t* __restrict__ plist, const uint32_t* __restrict__ cursor,
-                                                                int cap, uint32_t* __restrict__ S, uint32_t* __restrict__ pc,
-                                                                uint32_t* __restrict__ cnt, uint32_t* __restrict__ Gout,
-                                                                unsigned long long* __restrict__ seg_stats) {
-  extern __shared__ uint32_t s_k[];
+                                                                int cap, uint32_t key_base, uint32_t* __restrict__ S,
+                                                                uint32_t* __restrict__ pc, uint32_t* __restrict__ cnt,
+                                                                uint32_t* __restrict__ Gout, unsigned long long* __restrict__ seg_stats) {
+  extern __shared__ uint32_t s_k[];                        // [n2(cap)] sorted keys | [NB + 1] bucket offsets | u16 [BUCKET_SORT_MAX] ranks
   __shared__ uint32_t s_w[RANK_THREADS / 32];
+  __shared__ uint32_t s_mn, s_mx, s_big;
   const int seg = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const uint32_t np_all = cursor[seg];
   const bool overflow = np_all > (uint32_t)cap;
@@ -159,21 +142,83 @@ __global__ void __launch_bounds__(RANK_THREADS) pos_sort_kernel(const uint32_t* 
   if (tid == 0) {
     seg_stats[(size_t)seg * 4 + 0] = np_all;
     seg_stats[(size_t)seg * 4 + 3] = overflow ? 1ull : 0ull;
+    s_mn = 0xffffffffu; s_mx = 0u; s_big = 0u;
   }
   int n2 = 2;
   while (n2 < P) n2 <<= 1;
+  int n2cap = 2;
+  while (n2cap < cap) n2cap <<= 1;
   const uint32_t* src = plist + (size_t)seg * cap;
-  for (int i = tid; i < n2; i += RANK_THREADS) s_k[i] = i < P ? src[i] : 0xffffffffu;
-  __syncthreads();
-  for (int k = 2; k <= n2; k <<= 1) {
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int t = tid; t < (n2 >> 1); t += RANK_THREADS) {
-        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-        const uint32_t a = s_k[i], b = s_k[i + j];
-        const bool up = (i & k) == 0;
-        if ((a > b) == up) { s_k[i] = b; s_k[i + j] = a; }
+  bool sorted = false;
+  if (P > 64 && P <= BUCKET_SORT_MAX) {
+    uint32_t* s_off = s_k + n2cap;                                              // [NB + 1]
+    unsigned short* s_r = reinterpret_cast<unsigned short*>(s_off + BUCKET_SORT_NB + 1);   // [BUCKET_SORT_MAX]
+    uint32_t mn = 0xffffffffu, mx = 0u;
+    for (int i = tid; i < P; i += RANK_THREADS) { const uint32_t k = src[i]; mn = min(mn, k); mx = max(mx, k); }
+    mn = __reduce_min_sync(0xffffffffu, mn);
+    mx = __reduce_max_sync(0xffffffffu, mx);
+    for (int i = tid; i <= BUCKET_SORT_NB; i += RANK_THREADS) s_off[i] = 0u;
+    __syncthreads();
+    if (lane == 0) { atomicMin(&s_mn, mn); atomicMax(&s_mx, mx); }
+    __syncthreads();
+    LinIndex li;
+    li.init(s_mn, s_mx, BUCKET_SORT_NB, key_base);
+    for (int i = tid; i < P; i += RANK_THREADS) s_r[i] = (unsigned short)atomicAdd(&s_off[li(src[i])], 1u);
+    __syncthreads();
+    // exclusive scan of the bucket sizes (thread t: buckets [8t, 8t + 8)), largest bucket
+    constexpr int BPT = BUCKET_SORT_NB / RANK_THREADS;
+    uint32_t c[BPT], sum = 0, big = 0;
+#pragma unroll
+    for (int j = 0; j < BPT; ++j) { c[j] = s_off[tid * BPT + j]; sum += c[j]; big = max(big, c[j]); }
+    uint32_t incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t n = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += n;
+    }
+    big = __reduce_max_sync(0xffffffffu, big);
+    if (lane == 31) s_w[w] = incl;
+    if (lane == 0) atomicMax(&s_big, big);
+    __syncthreads();
+    uint32_t off = incl - sum;
+    for (int i = 0; i < w; ++i) off += s_w[i];
+#pragma unroll
+    for (int j = 0; j < BPT; ++j) { s_off[tid * BPT + j] = off; off += c[j]; }
+    if (tid == RANK_THREADS - 1) s_off[BUCKET_SORT_NB] = off;
+    __syncthreads();
+    for (int i = tid; i < P; i += RANK_THREADS) { const uint32_t k = src[i]; s_k[s_off[li(k)] + s_r[i]] = k; }
+    __syncthreads();
+    if (s_big <= (uint32_t)BUCKET_SORT_RUN) {
+#pragma unroll 1
+      for (int j = 0; j < BPT; ++j) {
+        const int b0 = (int)s_off[tid * BPT + j], b1 = (int)s_off[tid * BPT + j + 1];
+        for (int i = b0 + 1; i < b1; ++i) {
+          const uint32_t k = s_k[i];
+          int m = i - 1;
+          while (m >= b0 && s_k[m] > k) { s_k[m + 1] = s_k[m]; --m; }
+          s_k[m + 1] = k;
+        }
       }
-      __syncthreads();
+      sorted = true;
+    } else {
+      for (int i = P + tid; i < n2; i += RANK_THREADS) s_k[i] = 0xffffffffu;   // pad for the network below
+    }
+    __syncthreads();
+  } else {
+    for (int i = tid; i < n2; i += RANK_THREADS) s_k[i] = i < P ? src[i] : 0xffffffffu;
+    __syncthreads();
+  }
+  if (!sorted) {
+    for (int k = 2; k <= n2; k <<= 1) {
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        for (int t = tid; t < (n2 >> 1); t += RANK_THREADS) {
+          const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+          const uint32_t a = s_k[i], b = s_k[i + j];
+          const bool up = (i & k) == 0;
+          if ((a > b) == up) { s_k[i] = b; s_k[i + j] = a; }
+        }
+        __syncthreads();
+      }
     }
   }
   // distinct values: thread t owns the contiguous slice [t * per, (t + 1) * per) of the sorted list
@@ -235,7 +280,7 @@ __global__ void __launch_bounds__(RANK_THREADS, 1) rank_kernel(const float* __re
   extern __shared__ __align__(16) unsigned char s_raw[];
   uint32_t* s_S = reinterpret_cast<uint32_t*>(s_raw);                       // [pass_cap]
   uint32_t* s_cnt = s_S + pass_cap;                                          // [2 * pass_cap + 2]
-  unsigned short* s_lut = reinterpret_cast<unsigned short*>(s_cnt + 2 * pass_cap + 2);   // [RANK_LUT + 2]
+  uint32_t* s_lut = s_cnt + 2 * pass_cap + 2;                                // [RANK_LUT]
   __shared__ unsigned s_c[2][RANK_THREADS / 32];
   const int seg = blockIdx.y, tid = threadIdx.x;
   const size_t base = (size_t)seg * (size_t)seg_len;
@@ -261,26 +306,10 @@ __global__ void __launch_bounds__(RANK_THREADS, 1) rank_kernel(const float* __re
     // ---- stage this pass's positives, zero its counters, build the index table ------------------------------
     for (int i = tid; i < gn; i += RANK_THREADS) s_S[i] = Sg[g0 + i];
     for (int i = tid; i < 2 * gn + 2; i += RANK_THREADS) s_cnt[i] = 0u;
-    const uint32_t s_first = gn > 0 ? Sg[g0] : 0u, s_last = gn > 0 ? Sg[g0 + gn - 1] : 0u;
     const uint32_t s_prev = g0 > 0 ? Sg[g0 - 1] : 0u;
-    const float f_lo = key_float(s_first, key_base), f_hi = key_float(s_last, key_base);
-    const float scale = (gn > 1 && f_hi > f_lo) ? __fdiv_rn((float)RANK_LUT, __fsub_rn(f_hi, f_lo)) : 0.f;
-    auto qidx = [&](float f) {
-      const int q = __float2int_rz(__fmul_rn(__fsub_rn(f, f_lo), scale));
-      return min(max(q, 0), RANK_LUT - 1);
-    };
     __syncthreads();
-    // lut[q] = first local group whose index value is >= q (q = 0 .. RANK_LUT); monotone in the key, so the
-    // lower bound of a key with index q lies in [lut[q], lut[q + 1]]
-    for (int q = tid; q <= RANK_LUT; q += RANK_THREADS) {
-      int lo = 0, hi = gn;
-      while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (qidx(key_float(s_S[mid], key_base)) < q) lo = mid + 1; else hi = mid;
-      }
-      s_lut[q] = (unsigned short)lo;
-    }
-    __syncthreads();
+    SmemTable tab;
+    tab.build(s_S, s_lut, gn, key_base);
 
     for (long long q = v0 + tid; q < v1; q += RANK_THREADS) {
       const size_t i = base + (size_t)q * VEC;
@@ -290,10 +319,10 @@ __global__ void __launch_bounds__(RANK_THREADS, 1) rank_kernel(const float* __re
         const float4 t = *reinterpret_cast<const float4*>(values + i);
         v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
         if (pos_u8 || sizeof(GT) == 1) {
-          const uchar4 g = *reinterpret_cast<const uchar4*>((pos_u8 ? pos_u8 : reinterpret_cast<const uint8_t*>(gt)) + i);
-          const unsigned char gg[4] = {g.x, g.y, g.z, g.w};
+          const uint32_t g = *reinterpret_cast<const uint32_t*>((pos_u8 ? pos_u8 : reinterpret_cast<const uint8_t*>(gt)) + i);
+          const uint32_t pm = positive_bytes(g, out_mask, pos_u8 != nullptr);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) pos[j] = pos_u8 ? (gg[j] != 0) : (gg[j] < 64 && ((out_mask >> gg[j]) & 1ull));
+          for (int j = 0; j < 4; ++j) pos[j] = ((pm >> (8 * j)) & 1u) != 0u;
         } else {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -360,19 +389,10 @@ __global__ void __launch_bounds__(RANK_THREADS, 1) rank_kernel(const float* __re
       for (int j = 0; j < VEC; ++j) {
         sk[j] = key[j] >> 1;
         act[j] = !pos[j] && !bad[j];
-        const int qq = qidx(key_float(sk[j], key_base));
-        lo[j] = s_lut[qq];
-        hi[j] = s_lut[qq + 1];
+        tab.range(sk[j], lo[j], hi[j]);
       }
 #pragma unroll
-      for (int j = 0; j < VEC; ++j) {
-        int l = lo[j], h = hi[j];
-        while (l < h) {
-          const int mid = (l + h) >> 1;
-          if (s_S[mid] < sk[j]) l = mid + 1; else h = mid;
-        }
-        lo[j] = l;
-      }
+      for (int j = 0; j < VEC; ++j) lo[j] = tab.finish(sk[j], lo[j], hi[j]);
 #pragma unroll
       for (int j = 0; j < VEC; ++j) {
         const int l = lo[j];
@@ -512,6 +532,22 @@ __global__ void __launch_bounds__(RANK_THREADS) rank_scan_kernel(const uint32_t*
   results[seg] = o;
 }
 
+// positives of every segment of the last dml_ood_rank_segments call -> appended to one list (pooled metric)
+__global__ void __launch_bounds__(256) export_positives_kernel(const uint32_t* __restrict__ plist, const uint32_t* __restrict__ cursor,
+                                                               int cap, uint32_t* __restrict__ out, long long out_capacity,
+                                                               unsigned long long* __restrict__ count) {
+  __shared__ unsigned long long s_base;
+  const int seg = blockIdx.x;
+  const uint32_t np_all = cursor[seg];
+  const uint32_t P = np_all > (uint32_t)cap ? 0u : np_all;   // an overflowed segment exports nothing: the count then falls short
+  if (threadIdx.x == 0) s_base = atomicAdd(count, (unsigned long long)P);
+  __syncthreads();
+  const unsigned long long base = s_base;
+  if (base + P > (unsigned long long)out_capacity) return;
+  const uint32_t* src = plist + (size_t)seg * cap;
+  for (uint32_t i = threadIdx.x; i < P; i += blockDim.x) out[base + i] = src[i];
+}
+
 }  // namespace
 }  // namespace dml
 
@@ -574,13 +610,11 @@ int dml_ood_rank_segments(const float* values, const float* minmax, int32_t minm
   {
     int n2 = 2;
     while (n2 < pos_capacity) n2 <<= 1;
-    const size_t smem = (size_t)n2 * sizeof(uint32_t);
-    static bool attr_done = false;   // idempotent; a race only repeats the call
-    if (!attr_done) {
-      DML_CUDA_TRY(cudaFuncSetAttribute(pos_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RANK_SORT_MAX * (int)sizeof(uint32_t)));
-      attr_done = true;
-    }
-    pos_sort_kernel<<<n_seg, RANK_THREADS, smem, stream>>>(plist, cursor, pos_capacity, S, pc, cnt, G, st);
+    // sorted keys | bucket offsets | per-key ranks of the bucket sort (<= 128 KB + 32 KB + 32 KB)
+    const size_t smem = (size_t)n2 * sizeof(uint32_t) + (size_t)(BUCKET_SORT_NB + 1) * sizeof(uint32_t) +
+                        (size_t)BUCKET_SORT_MAX * sizeof(unsigned short) + 16;
+    DML_CUDA_TRY(cudaFuncSetAttribute(pos_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    pos_sort_kernel<<<n_seg, RANK_THREADS, smem, stream>>>(plist, cursor, pos_capacity, key_base, S, pc, cnt, G, st);
     DML_LAUNCH_CHECK();
   }
   // 3. rank
@@ -588,7 +622,7 @@ int dml_ood_rank_segments(const float* values, const float* minmax, int32_t minm
     // positives of one pass: as many as fit next to their counters and the index table in 227 KB of shared memory
     int pass_cap = pos_capacity < 12288 ? pos_capacity : 12288;
     pass_cap = (pass_cap + 3) & ~3;
-    const size_t smem = (size_t)pass_cap * 4 + ((size_t)2 * pass_cap + 2) * 4 + (size_t)(RANK_LUT + 2) * 2 + 16;
+    const size_t smem = (size_t)pass_cap * 4 + ((size_t)2 * pass_cap + 2) * 4 + SmemTable::lut_bytes() + 16;
     auto al = [](const void* q, size_t a) { return q == nullptr || (reinterpret_cast<uintptr_t>(q) % a) == 0; };
     const bool vec4 = (seg_len % 4 == 0) && al(values, 16) && al(keys_out, 16) && al(conf_out, 16) && al(msp, 16) &&
                       al(msp_norm_out, 16) && al(mix_out, 16) && al(gt_u8, 4) && al(pos_u8, 4);
@@ -620,6 +654,21 @@ int dml_ood_rank_segments(const float* values, const float* minmax, int32_t minm
   }
   // 4. scan
   rank_scan_kernel<<<n_seg, RANK_THREADS, 0, stream>>>(pc, cnt, G, pos_capacity, seg_len, st, recall_level, results);
+  DML_LAUNCH_CHECK();
+  return DML_OK;
+}
+
+int dml_ood_rank_export_positives(const void* rank_workspace, size_t workspace_bytes, int32_t n_seg, int32_t pos_capacity,
+                                  uint32_t* out, int64_t out_capacity, long long* count, dml_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!rank_workspace || !count || n_seg < 0 || pos_capacity < 1 || out_capacity < 0 || (out_capacity > 0 && !out)) return DML_ERR_INVALID_ARG;
+  if (n_seg == 0) return DML_OK;
+  const RankWs w = make_rank_ws(n_seg, pos_capacity);
+  if (workspace_bytes < w.off_end) return DML_ERR_WORKSPACE;
+  const unsigned char* ws = reinterpret_cast<const unsigned char*>(rank_workspace);
+  export_positives_kernel<<<n_seg, 256, 0, stream>>>(reinterpret_cast<const uint32_t*>(ws + w.off_plist),
+                                                     reinterpret_cast<const uint32_t*>(ws + w.off_cursor), pos_capacity, out,
+                                                     out_capacity, (unsigned long long*)count);
   DML_LAUNCH_CHECK();
   return DML_OK;
 }

@@ -9,23 +9,6 @@ import torch
 from ..head import confusion_counts
 
 
-class _StreamMetrics(object):
-    def __init__(self):
-        raise NotImplementedError()
-
-    def update(self, gt, pred):
-        raise NotImplementedError()
-
-    def get_results(self):
-        raise NotImplementedError()
-
-    def to_str(self, metrics):
-        raise NotImplementedError()
-
-    def reset(self):
-        raise NotImplementedError()
-
-
 def _labels_cuda(a, device=None):
     t = a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(np.asarray(a)))
     if t.dtype not in (torch.uint8, torch.int64):
@@ -35,7 +18,7 @@ def _labels_cuda(a, device=None):
     return t
 
 
-class StreamSegMetrics(_StreamMetrics):
+class StreamSegMetrics:
     """Same interface as the reference: ``update(label_trues, label_preds)``, ``get_results()`` ->
     dict(Overall Acc, Mean Acc, FreqW Acc, Mean IoU, Class IoU), ``to_str``, ``reset``.
     Like the reference, ``n_classes`` is pinned to 19 regardless of the constructor argument (:30)."""
@@ -67,55 +50,27 @@ class StreamSegMetrics(_StreamMetrics):
 
     @staticmethod
     def to_str(results):
-        string = "\n"
-        for k, v in results.items():
-            if k != "Class IoU":
-                string += "%s: %f\n" % (k, v)
-        return string
+        """one ``name: value`` line per scalar entry (the per-class dict is skipped), stream_metrics.py:36-47"""
+        return "\n" + "".join("%s: %f\n" % (k, v) for k, v in results.items() if k != "Class IoU")
 
     def get_results(self):
+        """Overall / mean-class / frequency-weighted accuracy and IoU from the 19 x 19 counts (rows = ground truth);
+        classes that never occur give NaN and are skipped by the nan-means, as in stream_metrics.py:57-81."""
         hist = self.sync()
+        tp = np.diag(hist)
+        gt_n, pred_n, total = hist.sum(axis=1), hist.sum(axis=0), hist.sum()
         with np.errstate(divide="ignore", invalid="ignore"):
-            acc = np.diag(hist).sum() / hist.sum()
-            acc_cls = np.nanmean(np.diag(hist) / hist.sum(axis=1))
-            iu = np.diag(hist) / (hist.sum(axis=1) + hist.sum(axis=0) - np.diag(hist))
-            mean_iu = np.nanmean(iu)
-            freq = hist.sum(axis=1) / hist.sum()
-            fwavacc = (freq[freq > 0] * iu[freq > 0]).sum()
-        print(iu)
-        cls_iu = dict(zip(range(self.n_classes), iu))
-        return {"Overall Acc": acc, "Mean Acc": acc_cls, "FreqW Acc": fwavacc, "Mean IoU": mean_iu, "Class IoU": cls_iu}
+            iu = tp / (gt_n + pred_n - tp)
+            res = {"Overall Acc": tp.sum() / total, "Mean Acc": np.nanmean(tp / gt_n)}
+            freq = gt_n / total
+            seen = freq > 0
+            res["FreqW Acc"] = (freq[seen] * iu[seen]).sum()
+            res["Mean IoU"] = np.nanmean(iu)
+        print(iu)                                  # the reference prints the per-class IoU vector (:76)
+        res["Class IoU"] = dict(zip(range(self.n_classes), iu))
+        return res
 
     def reset(self):
         self.confusion_matrix = np.zeros((self.n_classes, self.n_classes))
         if self._conf is not None:
             self._conf.zero_()
-
-
-class AverageMeter(object):
-    """metrics/stream_metrics.py:86-111 (host bookkeeping)."""
-
-    def __init__(self):
-        self.book = dict()
-
-    def reset_all(self):
-        self.book.clear()
-
-    def reset(self, id):
-        item = self.book.get(id, None)
-        if item is not None:
-            item[0] = 0
-            item[1] = 0
-
-    def update(self, id, val):
-        record = self.book.get(id, None)
-        if record is None:
-            self.book[id] = [val, 1]
-        else:
-            record[0] += val
-            record[1] += 1
-
-    def get_results(self, id):
-        record = self.book.get(id, None)
-        assert record is not None
-        return record[0] / record[1]

@@ -116,6 +116,24 @@ class CudaOps:
                                            ptr(partial), stream_ptr(self.device)), "dml_ood_scan_range")
         return partial
 
+    # ---- minority-rank building blocks (ood.rank_keys split at its collective points) ---------------------------
+    def sorted_positive_keys(self, keys, n_pos):
+        return ood.sorted_positive_keys(keys, n_pos, self.ws, "d_pr")
+
+    def sort31(self, keys, tag):
+        return ood.sort_keys(keys, self.ws, "d_" + tag, end_bit=31)
+
+    def unique_groups(self, sorted_pos):
+        return ood.unique_groups(sorted_pos, self.ws, "d_pr")
+
+    def bucket_rank_counters(self, keys, S, key_base):
+        if S.numel() > ood.MAX_RANK_GROUPS:
+            raise ValueError("pooled_measures(mode='rank'): too many distinct positive scores; use mode='partition'")
+        return ood.bucket_rank_counters(keys, S, key_base, self.ws, "d_pr")
+
+    def pooled_scan(self, pc, cnt, total_pos, total_n, n_nan, recall_level):
+        return ood.pooled_scan(pc, cnt, total_pos, total_n, n_nan, recall_level, self.ws, "d_pr")
+
     def empty_keys(self, n, tag):
         return self.ws.get("d_recv_" + tag, 4 * max(n, 1)).view(torch.int32)[:n]
 
@@ -175,12 +193,14 @@ def pooled_measures(conf: torch.Tensor, gt: torch.Tensor, out_labels: Sequence[i
     ``keys_and_stats`` = (packed keys int32 [n], stats int64 [>=3] = n_pos, n_nan, n_out_of_window), e.g. an
     ``ood.KeyPool``'s ``keys`` / ``stats[0]`` filled by the per-image evaluation: the rank's key generation is skipped
     (``conf`` / ``gt`` may then be None); the keys may be in any order."""
-    if mode not in ("partition", "alltoall", "allgather"):
-        raise ValueError("mode must be 'partition', 'alltoall' or 'allgather'")
+    if mode not in ("partition", "alltoall", "allgather", "rank"):
+        raise ValueError("mode must be 'partition', 'alltoall', 'allgather' or 'rank'")
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     dev = conf.device if keys_and_stats is None else keys_and_stats[0].device
     ops = ops or CudaOps(dev, workspace)
+    if mode == "rank":
+        return _pooled_measures_rank(conf, gt, out_labels, group, recall_level, ops, key_base, timing, keys_and_stats)
     marks = []
 
     def mark(name):
@@ -287,6 +307,91 @@ def pooled_measures(conf: torch.Tensor, gt: torch.Tensor, out_labels: Sequence[i
         marks[-1][1].synchronize()
         out["phase_ms"] = {b[0]: a[1].elapsed_time(b[1]) for a, b in zip(marks[:-1], marks[1:])}
     return auroc, aupr, fpr, out
+
+
+def _pooled_measures_rank(conf, gt, out_labels, group, recall_level, ops, key_base, timing, keys_and_stats):
+    """``pooled_measures(mode="rank")``: the minority-rank form of the pooled metric.  No negative ever leaves its GPU:
+
+      1. every rank compacts and radix-sorts the score keys of ITS positives (~1 % of the pairs);
+      2. the locally sorted shards are all-gathered (NCCL) and merged on every rank into the distinct positive scores
+         S[g] with multiplicities pc[g] -- identical on all ranks;
+      3. every rank buckets its negatives by S and locates them in shared memory (``dml_ood_bucket_rank``): counters
+         bt[g] / eq[g] of its own pixels;
+      4. one all-reduce (exact int64 sums) of the 2G + 2 counters, then the same scan over the G groups on every rank
+         -> bit-identical (auroc, aupr, fpr) everywhere, equal to the single-GPU result.
+
+    Exchanged per rank: the positives (4 B each) and 16 B per distinct positive score, instead of 4 B for every pair."""
+    world = dist.get_world_size(group)
+    dev = conf.device if keys_and_stats is None else keys_and_stats[0].device
+    marks = []
+
+    def mark(name):
+        if timing and dev.type == "cuda":
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record(torch.cuda.current_stream(dev))
+            marks.append((name, ev))
+
+    mark("start")
+    pos_keys = pos_count = None
+    if keys_and_stats is None:
+        keys, stats = ops.make_keys(conf, gt, out_labels, key_base)
+    else:
+        keys, stats = keys_and_stats[:2]
+        keys, stats = keys.contiguous().view(-1), stats.view(-1)
+        if len(keys_and_stats) == 4:          # (.., KeyPool.pos, KeyPool.pos_count): positives gathered by the rank batches
+            pos_keys, pos_count = keys_and_stats[2:]
+    mark("keygen")
+    n_local = keys.numel()
+    # local counts -> every rank (one small all_gather; the host needs them to size the exchange)
+    have = pos_count.view(-1)[:1].to(torch.int64) if pos_count is not None else torch.full((1,), -1, dtype=torch.int64, device=dev)
+    mine = torch.cat([stats[:3].to(torch.int64), torch.tensor([n_local], dtype=torch.int64, device=dev), have])
+    allc = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(allc, mine, group=group)
+    allc = torch.stack(allc).cpu()                                      # [rank, (n_pos, n_nan, n_oow, n, positives on hand)]
+    total_pos, n_nan, n_oow, total_n = [int(v) for v in allc[:, :4].sum(0).tolist()]
+    if n_nan:
+        raise ValueError("Input contains NaN.")
+    if n_oow:
+        raise ValueError("pooled_measures: conf must be non-negative (keys left the packed 31-bit window)")
+    pos_counts = [int(v) for v in allc[:, 0].tolist()]
+    mark("counts_exchange")
+    me = dist.get_rank(group)
+    if pos_keys is not None and int(allc[me, 4]) == pos_counts[me] and pos_counts[me] <= pos_keys.numel():
+        srt = ops.sort31(pos_keys[: pos_counts[me]], "rk_local")                # the list the per-image pass left
+    else:
+        srt = ops.sorted_positive_keys(keys, pos_counts[me])                    # int32 [n_pos_local], ascending
+    mark("local_positive_sort")
+    pmax = max(pos_counts) if pos_counts else 0
+    out = {"n_pos": total_pos, "n_neg": total_n - total_pos, "n_groups": -1, "mode": "rank",
+           "exchanged_bytes": 4 * (sum(pos_counts) - pos_counts[dist.get_rank(group)])}
+    if total_pos == 0 or total_pos == total_n:
+        return float("nan"), float("nan"), float("nan"), out
+    pad = ops.empty_keys(pmax, "rk_pad")
+    pad[: srt.numel()].copy_(srt)
+    shards = [ops.empty_keys(pmax, f"rk_shard{r}") for r in range(world)]
+    dist.all_gather(shards, pad, group=group)
+    allpos = ops.empty_keys(total_pos, "rk_all")
+    off = 0
+    for r in range(world):
+        allpos[off: off + pos_counts[r]].copy_(shards[r][: pos_counts[r]])
+        off += pos_counts[r]
+    mark("positive_allgather")
+    merged = ops.sort31(allpos, "rk_merge")
+    S, pc, G = ops.unique_groups(merged)
+    mark("merge_positives")
+    cnt = ops.bucket_rank_counters(keys, S, key_base)
+    mark("bucket_rank")
+    dist.all_reduce(cnt, group=group)
+    out["exchanged_bytes"] += 8 * cnt.numel()
+    mark("counter_allreduce")
+    res = ops.pooled_scan(pc, cnt, total_pos, total_n, n_nan, recall_level)
+    r = res.cpu().numpy()
+    mark("scan")
+    out["n_pos_groups"] = G
+    if marks:
+        marks[-1][1].synchronize()
+        out["phase_ms"] = {b[0]: a[1].elapsed_time(b[1]) for a, b in zip(marks[:-1], marks[1:])}
+    return float(r[0, 0]), float(r[0, 1]), float(r[0, 2]), out
 
 
 def mean_of_per_image(per_image_vals: torch.Tensor, group=None):

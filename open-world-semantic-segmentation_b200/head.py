@@ -173,6 +173,33 @@ def dml_head(x: torch.Tensor, centers: Optional[torch.Tensor] = None, magnitude:
     return o
 
 
+def conv1x1_head(features: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None,
+                 magnitude: float = DEFAULT_MAGNITUDE, want_embedding: bool = True, want_logits: bool = True):
+    """Final 1x1 classifier conv + distance block in one kernel (``dml_conv1x1_head_forward``):
+    ``features`` [B,C,h,w] fp32 CUDA (the input of ``conv_last[4]`` / ``classifier[3]``), ``weight`` [K,C] or
+    [K,C,1,1], ``bias`` [K] or None.  Returns ``(embedding [B,K,h,w] or None, logits [B,K,h,w] or None)`` --
+    anomaly/models/models.py:609,636-657; inference only (no autograd)."""
+    require_cuda(features, "features")
+    if features.dtype != torch.float32 or features.dim() != 4:
+        raise ValueError("features must be a float32 [B,C,h,w] tensor")
+    features = features.contiguous()
+    B, Cc, Hh, Ww = features.shape
+    dev = features.device
+    w = weight.detach().to(device=dev, dtype=torch.float32).reshape(weight.shape[0], -1).contiguous()
+    if w.shape[1] != Cc:
+        raise ValueError(f"weight must be [K,{Cc}] (or [K,{Cc},1,1])")
+    K = w.shape[0]
+    bvec = None if bias is None else bias.detach().to(device=dev, dtype=torch.float32).contiguous()
+    if bvec is not None and bvec.numel() != K:
+        raise ValueError("bias must have K entries")
+    emb = torch.empty(B, K, Hh, Ww, dtype=torch.float32, device=dev) if want_embedding else None
+    logits = torch.empty(B, K, Hh, Ww, dtype=torch.float32, device=dev) if want_logits else None
+    with torch.cuda.device(dev):
+        check(lib().dml_conv1x1_head_forward(ptr(features), ptr(w), ptr(bvec), magnitude, B, Cc, K, Hh, Ww, ptr(emb), ptr(logits),
+                                             stream_ptr(dev)), "dml_conv1x1_head_forward")
+    return emb, logits
+
+
 def dml_multiscale_head(z_list, size, *, reciprocal_average: bool = False, want_scores: bool = False,
                         label_dtype: Optional[torch.dtype] = torch.uint8, want_maxlogit: bool = False,
                         want_eds: bool = False, eds_clamp: float = 0.0, want_msp: bool = False,

@@ -75,6 +75,10 @@ class KeyPool:
         # by distributed.pooled_measures(keys_and_stats=...), so a local pooled histogram would be of no use)
         self.scratch = self.ws.get("pool_scratch", lib().dml_ood_workspace_bytes(1, self.capacity)) if histograms else None
         self.stats = torch.zeros(1, 4, dtype=torch.int64, device=self.device)
+        # score keys of the positives the minority-rank batches gathered anyway (method="rank"): the pooled rank
+        # evaluation then skips its compaction pass over all keys.  Allocated by the first such batch.
+        self.pos = None
+        self.pos_count = torch.zeros(1, dtype=torch.int64, device=self.device)
         self.reset()
 
     def reset(self):
@@ -82,6 +86,7 @@ class KeyPool:
         self.signature = None
         self.hist_ok = True      # every contribution so far also left its digit histograms (method="sort" batches)
         self.stats.zero_()
+        self.pos_count.zero_()
 
     def _take(self, n: int, signature) -> torch.Tensor:
         if self.n + n > self.capacity:
@@ -94,9 +99,17 @@ class KeyPool:
         self.n += n
         return view
 
-    def evaluate(self, recall_level: float = RECALL_LEVEL_DEFAULT):
+    def evaluate(self, recall_level: float = RECALL_LEVEL_DEFAULT, method: str = "sort"):
         """(results [1,7] float64, stats [1,4] int64) device tensors of the pooled segment, like ``eval_segments``.
-        The pool must be full (``capacity`` keys): the pooled histogram slot belongs to that segment length."""
+        method="sort": radix sort of all pooled keys + scan; the pool must be full (``capacity`` keys): the pooled
+        histogram slot belongs to that segment length.  method="rank": ``rank_keys`` -- only the positives are sorted,
+        the negatives are grouped by bucket and located among them (two small host synchronisations)."""
+        if method not in ("sort", "rank"):
+            raise ValueError("method must be 'sort' or 'rank'")
+        if method == "rank":
+            key_base = self.signature[0] if self.signature is not None else KEY_BASE_NONNEG
+            return rank_keys(self.keys[: self.n], self.stats, key_base, recall_level, self.ws, pos_keys=self.pos,
+                             pos_count=self.pos_count), self.stats
         if self.scratch is None:
             raise ValueError("KeyPool(histograms=False) only collects keys; evaluate them with distributed.pooled_measures")
         if self.n != self.capacity:
@@ -265,7 +278,126 @@ def _eval_segments_rank(values, n_seg, seg_len, gt, out_labels, positive, score_
             pool.hist_ok = False       # this batch left keys and counts, no digit histograms
             check(lib().dml_ood_pool_histograms(None, 0, ptr(stats), n_seg, seg_len, None, 0, pool.capacity, ptr(pool.stats),
                                                 1 if pool.n == n else 0, s), "dml_ood_pool_histograms")
+            if pool.pos is None:
+                pool.pos = torch.empty(max(1 << 20, pool.capacity // 16), dtype=torch.int32, device=dev)
+            check(lib().dml_ood_rank_export_positives(ptr(rws), rws.numel(), n_seg, pos_capacity, ptr(pool.pos), pool.pos.numel(),
+                                                      ptr(pool.pos_count), s), "dml_ood_rank_export_positives")
     return results, stats
+
+
+MAX_RANK_GROUPS = 4096 * 12288    # distinct positive scores dml_ood_bucket_rank can bucket
+
+
+def _i32(ws: "OodWorkspace", name: str, n: int) -> torch.Tensor:
+    return ws.get(name, 4 * max(int(n), 1)).view(torch.int32)[: max(int(n), 0)]
+
+
+def sorted_positive_keys(keys: torch.Tensor, n_pos: int, ws: "OodWorkspace", tag: str = "pr") -> torch.Tensor:
+    """Score keys (key >> 1) of the ``n_pos`` positives of ``keys`` (packed, bit 0 = positive), sorted ascending.
+    int32 tensor of u32 bit patterns (may alias workspace memory)."""
+    dev = keys.device
+    out = _i32(ws, tag + "_pos", n_pos)
+    cnt = ws.get(tag + "_count", 8).view(torch.int64)[:1]
+    with torch.cuda.device(dev):
+        s = stream_ptr(dev)
+        check(lib().dml_ood_pos_compact(ptr(keys), keys.numel(), ptr(out), n_pos, ptr(cnt), s), "dml_ood_pos_compact")
+        return sort_keys(out, ws, tag + "_sort", end_bit=31)
+
+
+def sort_keys(keys: torch.Tensor, ws: "OodWorkspace", tag: str, end_bit: int = 32) -> torch.Tensor:
+    """radix sort of u32 bit patterns (int32 tensor); returns the sorted tensor (``keys`` itself or workspace memory)"""
+    n = keys.numel()
+    if n == 0:
+        return keys
+    dev = keys.device
+    scratch = ws.get(tag, lib().dml_ood_workspace_bytes(1, n))
+    out = C.c_void_p()
+    with torch.cuda.device(dev):
+        check(lib().dml_ood_sort(ptr(keys), 1, n, 0, end_bit, ptr(scratch), scratch.numel(), C.byref(out), stream_ptr(dev)),
+              "dml_ood_sort")
+    if out.value == keys.data_ptr():
+        return keys
+    off = out.value - scratch.data_ptr()
+    return scratch[off: off + 4 * n].view(torch.int32)
+
+
+def unique_groups(sorted_pos: torch.Tensor, ws: "OodWorkspace", tag: str = "pr"):
+    """sorted score keys -> (S [G] distinct scores, pc [G] multiplicities, G).  One host synchronisation (G)."""
+    dev = sorted_pos.device
+    n = sorted_pos.numel()
+    S, pc = _i32(ws, tag + "_S", n), _i32(ws, tag + "_pc", n)
+    g_dev = ws.get(tag + "_G", 8).view(torch.int64)[:1]
+    scratch = ws.get(tag + "_uniq", lib().dml_ood_unique_workspace_bytes(n))
+    with torch.cuda.device(dev):
+        check(lib().dml_ood_unique_counts(ptr(sorted_pos), n, ptr(S), ptr(pc), ptr(g_dev), ptr(scratch), scratch.numel(),
+                                          stream_ptr(dev)), "dml_ood_unique_counts")
+    G = int(g_dev.item())
+    return S[:G], pc[:G], G
+
+
+def bucket_rank_counters(keys: torch.Tensor, S: torch.Tensor, key_base: int, ws: "OodWorkspace", tag: str = "pr") -> torch.Tensor:
+    """int64 [2G + 2] counters of the negatives of ``keys`` against the sorted distinct positive scores ``S``
+    (``dml_ood_bucket_rank``); counters of disjoint key sets add (multi-GPU: one all_reduce)."""
+    dev = keys.device
+    n, G = keys.numel(), S.numel()
+    cnt = ws.get(tag + "_cnt", 8 * (2 * G + 2)).view(torch.int64)[: 2 * G + 2]
+    scratch = ws.get(tag + "_bucket", lib().dml_ood_bucket_rank_workspace_bytes(n, G))
+    with torch.cuda.device(dev):
+        check(lib().dml_ood_bucket_rank(ptr(keys), n, ptr(S), G, key_base, ptr(cnt), ptr(scratch), scratch.numel(),
+                                        stream_ptr(dev)), "dml_ood_bucket_rank")
+    return cnt
+
+
+def pooled_scan(pc: torch.Tensor, cnt: torch.Tensor, total_pos: int, total_n: int, n_nan: int, recall_level: float,
+                ws: "OodWorkspace", tag: str = "pr") -> torch.Tensor:
+    """[1,7] float64 result row (auroc, aupr, fpr, n_pos, n_neg, n_nan, -1) from the group counts / counters"""
+    dev = ws.device
+    G = pc.numel()
+    res = ws.get(tag + "_result", 8 * OOD_RESULT_WORDS).view(torch.float64)[:OOD_RESULT_WORDS].view(1, OOD_RESULT_WORDS)
+    scratch = ws.get(tag + "_scan", lib().dml_ood_pooled_scan_workspace_bytes(G))
+    with torch.cuda.device(dev):
+        check(lib().dml_ood_pooled_scan(ptr(pc) if G else None, ptr(cnt) if G else None, G, total_pos, total_n, n_nan,
+                                        recall_level, ptr(scratch), scratch.numel(), ptr(res), stream_ptr(dev)),
+              "dml_ood_pooled_scan")
+    return res
+
+
+def rank_keys(keys: torch.Tensor, stats: torch.Tensor, key_base: int = KEY_BASE_NONNEG,
+              recall_level: float = RECALL_LEVEL_DEFAULT, workspace: Optional["OodWorkspace"] = None,
+              pos_keys: Optional[torch.Tensor] = None, pos_count: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Exact metrics of ONE ranking given as packed keys (int32 tensor of u32 bit patterns, any order; e.g. a
+    ``KeyPool``) without sorting its negatives: positives compacted + sorted + de-duplicated, negatives bucketed and
+    located among them, scan over the positive groups (csrc/ood_pool_rank.cu).  ``stats``: int64 [.., 4] device tensor
+    whose first row starts with (n_pos, n_nan, ...).  Returns the [1,7] float64 device row of ``eval_segments``
+    (n_groups = -1).  Two host synchronisations (n_pos, number of distinct positive scores); falls back to the sort
+    path when the positives have more than 4096 * 12288 distinct scores.  ``pos_keys`` / ``pos_count``: score keys of
+    the positives collected beforehand (``KeyPool.pos``); used when they are complete, else the keys are compacted."""
+    require_cuda(keys, "keys")
+    keys = keys.contiguous().view(-1)
+    dev = keys.device
+    ws = workspace or OodWorkspace(dev)
+    n = keys.numel()
+    head = stats.view(-1)[:2] if pos_count is None else torch.cat([stats.view(-1)[:2], pos_count.view(-1)[:1]])
+    hv = [int(v) for v in head.tolist()]
+    n_pos, n_nan = hv[0], hv[1]
+    if n_pos <= 0 or n_pos >= n:
+        return pooled_scan(keys[:0], keys[:0], n_pos, n, n_nan, recall_level, ws)
+    if pos_keys is not None and pos_count is not None and hv[2] == n_pos and n_pos <= pos_keys.numel():
+        srt = sort_keys(pos_keys[:n_pos], ws, "pr_sort", end_bit=31)
+    else:
+        srt = sorted_positive_keys(keys, n_pos, ws)
+    S, pc, G = unique_groups(srt, ws)
+    if G > MAX_RANK_GROUPS:
+        res = ws.get("pr_result", 8 * OOD_RESULT_WORDS).view(torch.float64)[:OOD_RESULT_WORDS].view(1, OOD_RESULT_WORDS)
+        scratch = ws.get("pr_fallback", lib().dml_ood_workspace_bytes(1, n))
+        st = stats.view(-1)[:4].view(1, 4).contiguous()
+        work = keys.clone()
+        with torch.cuda.device(dev):
+            check(lib().dml_ood_eval_segments(ptr(work), ptr(st), 1, n, recall_level, ptr(scratch), scratch.numel(), 0,
+                                              ptr(res), stream_ptr(dev)), "dml_ood_eval_segments")
+        return res
+    cnt = bucket_rank_counters(keys, S, key_base, ws)
+    return pooled_scan(pc, cnt, n_pos, n, n_nan, recall_level, ws)
 
 
 def roc_fpr_after_eval(workspace: "OodWorkspace", n_seg: int, seg_len: int,

@@ -96,3 +96,61 @@ class NumpyOps:
 
     def empty_keys(self, n, tag):
         return torch.empty(n, dtype=torch.int32)
+
+    # ---- minority-rank mode (distributed.pooled_measures(mode="rank")): NumPy restatement of csrc/ood_pool_rank.cu ----
+    def sorted_positive_keys(self, keys, n_pos):
+        k = _u(keys)
+        return torch.from_numpy(np.sort(k[(k & 1) == 1] >> 1).astype(np.uint32).view(np.int32).copy())
+
+    def sort31(self, keys, tag):
+        return self.sort(keys, tag)
+
+    def unique_groups(self, sorted_pos):
+        s, c = np.unique(_u(sorted_pos), return_counts=True)
+        return (torch.from_numpy(s.astype(np.uint32).view(np.int32).copy()),
+                torch.from_numpy(c.astype(np.uint32).view(np.int32).copy()), int(s.size))
+
+    def bucket_rank_counters(self, keys, S, key_base):
+        k = _u(keys)
+        s = _u(S)
+        neg = (k[(k & 1) == 0] >> 1).astype(np.uint32)
+        lb = np.searchsorted(s, neg, side="left")
+        eq = (lb < s.size) & (s[np.minimum(lb, s.size - 1)] == neg)
+        cnt = np.bincount(2 * lb + eq, minlength=2 * s.size + 2).astype(np.int64)
+        return torch.from_numpy(cnt)
+
+    def pooled_scan(self, pc, cnt, total_pos, total_n, n_nan, recall_level):
+        pc = _u(pc).astype(np.int64)
+        c = cnt.numpy().astype(np.int64)
+        G, P, N = pc.size, int(total_pos), int(total_n - total_pos)
+        row = np.zeros(7, np.float64)
+        row.view(np.int64)[3:] = [P, N, n_nan, -1]
+        if P <= 0 or N <= 0 or G == 0:
+            row[:3] = np.nan
+            return torch.from_numpy(row.reshape(1, 7))
+        bt, eq, tail = c[0:2 * G:2], c[1:2 * G:2], int(c[2 * G])
+        T = np.cumsum(pc)
+        F = np.cumsum(bt + eq)
+        au = sum(int(b) * 2 * int(t - p) + int(e) * (2 * int(t) - int(p)) for b, e, t, p in zip(bt, eq, T, pc)) + 2 * P * tail
+        ap = 0.0
+        for p, t, f in zip(pc, T, F):
+            ap += float(p) * (float(t) / float(t + f))
+        tstar = min(P, max(0, int(np.floor(recall_level * P))))
+        while tstar < P and (tstar + 1) / P <= recall_level:
+            tstar += 1
+        while tstar > 0 and tstar / P > recall_level:
+            tstar -= 1
+        gs = int(np.searchsorted(T, tstar, side="right")) - 1          # last group with tps <= T*
+        da = db = float("inf")
+        a_fps = b_fps = 0
+        Tg, Fg = (int(T[gs]), int(F[gs])) if gs >= 0 else (0, 0)
+        trail = int(bt[gs + 1]) if gs + 1 <= G - 1 else 0
+        if gs >= 0 or trail > 0:
+            da, a_fps = abs(Tg / P - recall_level), Fg + trail
+        if gs + 1 <= G - 1:
+            trail = int(bt[gs + 2]) if gs + 2 <= G - 1 else 0
+            db, b_fps = abs(int(T[gs + 1]) / P - recall_level), int(F[gs + 1]) + trail
+        row[0] = au / (2.0 * P * N)
+        row[1] = ap / P
+        row[2] = (b_fps if db <= da else a_fps) / N
+        return torch.from_numpy(row.reshape(1, 7))

@@ -71,7 +71,9 @@ def _worker(rank, world, port, case, mode, q):
                                              (3, "skewed", "alltoall"), (3, "empty_rank", "allgather"), (2, "empty_rank", "alltoall"),
                                              (2, "plain", "partition"), (2, "ties", "partition"), (3, "skewed", "partition"),
                                              (3, "empty_rank", "partition"), (2, "ties+keys", "partition"),
-                                             (3, "empty_rank+keys", "partition"), (2, "plain+keys", "allgather")])
+                                             (3, "empty_rank+keys", "partition"), (2, "plain+keys", "allgather"),
+                                             (2, "plain", "rank"), (2, "ties", "rank"), (3, "skewed", "rank"),
+                                             (3, "empty_rank", "rank"), (2, "ties+keys", "rank")])
 def test_pooled_measures_gloo(world, case, mode):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
@@ -92,13 +94,16 @@ def test_pooled_measures_gloo(world, case, mode):
         assert (r[1], r[2], r[3]) == (first[1], first[2], first[3]), "ranks must agree bit-for-bit"
         np.testing.assert_allclose([r[1], r[2], r[3]], ref, rtol=0, atol=1e-12)
         assert r[4]["n_pos"] == int((gt == 13).sum()) and r[4]["n_neg"] == int((gt != 13).sum())
-        assert r[4]["n_groups"] == np.unique(conf).size
+        assert r[4]["n_groups"] == (np.unique(conf).size if mode != "rank" else -1)
         # per-image mean across ranks: NaN rows skipped, 2 images per rank counted
         exp = np.mean([[0.5 + 0.1 * k, 0.2, 0.3] for k in range(world)] + [[0.7, 0.4, 0.1]] * world, axis=0)
         np.testing.assert_allclose(r[5][:3], exp, rtol=1e-12)
         assert r[5][3] == 2 * world
         assert r[6] == [[sum(range(1, world + 1))] * 3] * 3
-    assert sum(r[4]["range_keys"] for r in results) == conf.size
+    if mode != "rank":
+        assert sum(r[4]["range_keys"] for r in results) == conf.size
+    else:
+        assert all(r[4]["n_pos_groups"] == np.unique(conf[gt == 13]).size for r in results)
 
 
 def test_choose_splitters_properties():

@@ -58,7 +58,7 @@ def _worker(rank, world, port, mode, q):
 
 
 @pytest.mark.parametrize("world", [1, 2])
-@pytest.mark.parametrize("mode", ["partition", "alltoall", "allgather", "partition+pool", "allgather+pool"])
+@pytest.mark.parametrize("mode", ["partition", "alltoall", "allgather", "partition+pool", "allgather+pool", "rank", "rank+pool"])
 def test_pooled_measures_nccl(world, mode):
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
@@ -79,7 +79,7 @@ def test_pooled_measures_nccl(world, mode):
     for r in results:
         assert (r[1], r[2], r[3]) == (results[0][1], results[0][2], results[0][3])
         np.testing.assert_allclose([r[1], r[2], r[3]], ref, rtol=0, atol=1e-12)
-        assert r[4]["n_groups"] == np.unique(conf).size
+        assert r[4]["n_groups"] == (np.unique(conf).size if not mode.startswith("rank") else -1)
 
 
 @pytest.mark.parametrize("n,n_buckets", [(0, 3), (1, 2), (4095, 1), (4097, 2), (100_003, 8), (1_000_000, 16), (300_000, 5)])

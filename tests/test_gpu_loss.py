@@ -135,6 +135,40 @@ def test_class_sums(nhwc, d, n_cls):
     assert np.array_equal(s2.cpu().numpy(), sums)
 
 
+@pytest.mark.parametrize("d,n_cls,h,w,kind", [(17, 19, 64, 96, "tiles"), (17, 19, 64, 96, "iid"), (16, 32, 48, 64, "rows"),
+                                               (13, 40, 40, 52, "iid"), (24, 19, 32, 64, "mixed"), (32, 19, 32, 32, "tiles")])
+def test_class_sums_label_patterns(d, n_cls, h, w, kind):
+    """the lane-owns-class kernel (n_cls <= 32; 4 pixels per thread when the row length allows it) on coherent tiles,
+    independent labels per pixel (its indexed-shuffle path), labels constant along rows, a mix, uint8 and int64
+    labels with ignored pixels; n_cls > 32 keeps the shared-memory kernel.  Exact counts, sums to 1e-6."""
+    from dml_b200 import prototypes as P
+    g = torch.Generator().manual_seed(d + n_cls + h)
+    b = 2
+    x = torch.randn(b, d, h, w, generator=g) * 2 + 0.5
+    if kind == "tiles":
+        lab = torch.randint(0, n_cls, (b, h // 16, w // 16), generator=g).repeat_interleave(16, 1).repeat_interleave(16, 2)
+    elif kind == "rows":
+        lab = torch.randint(0, n_cls, (b, h, 1), generator=g).expand(b, h, w).contiguous()
+    elif kind == "iid":
+        lab = torch.randint(0, n_cls, (b, h, w), generator=g)
+    else:
+        lab = torch.randint(0, n_cls, (b, h // 8, w // 8), generator=g).repeat_interleave(8, 1).repeat_interleave(8, 2)
+        noise = torch.rand(b, h, w, generator=g) < 0.3
+        lab = torch.where(noise, torch.randint(0, n_cls, (b, h, w), generator=g), lab)
+    lab = lab.clone()
+    lab[torch.rand(b, h, w, generator=g) < 0.1] = 255
+    for dtype in (torch.uint8, torch.int64):
+        sums, counts = P.class_sums(x.cuda(), lab.to(dtype).cuda(), n_cls)
+        sums, counts = sums.cpu().numpy(), counts.cpu().numpy()
+        for i in range(b):
+            feats = x[i].permute(1, 2, 0).reshape(-1, d).numpy()
+            rs, rc = O.per_class_sums(feats, lab[i].reshape(-1).numpy(), n_cls)
+            np.testing.assert_array_equal(counts[i], rc)
+            np.testing.assert_allclose(sums[i], rs, rtol=1e-6, atol=1e-3)
+        s2, _ = P.class_sums(x.cuda(), lab.to(dtype).cuda(), n_cls)
+        assert np.array_equal(s2.cpu().numpy(), sums)
+
+
 def test_novel_prototype_generation_recipe():
     """test_embedding.py:413-419: per support image, mean feature of the novel class if it covers > 5 %"""
     from dml_b200 import prototypes as P

@@ -164,3 +164,86 @@ def test_rank_full_size_images_equal_sort_path():
     assert torch.equal(conf_a, b.conf)
     assert np.array_equal(va[:, 0], vb[:, 0]) and np.array_equal(va[:, 2], vb[:, 2])
     np.testing.assert_allclose(va[:, 1], vb[:, 1], atol=1e-13)
+
+
+# ---------------------------------------------------------------------------------------------
+# pooled ranking (csrc/ood_pool_rank.cu): positives sorted, negatives bucketed + located, scan over the groups
+# ---------------------------------------------------------------------------------------------
+def _pooled_both(conf, gt, recall_level=0.95):
+    from dml_b200 import ood
+    n = conf.size
+    c, g = torch.from_numpy(conf.reshape(-1)).cuda(), torch.from_numpy(gt.reshape(-1)).cuda()
+    r1, s1 = ood.eval_segments(c, 1, n, gt=g, out_labels=(13,), recall_level=recall_level)
+    v1, c1 = ood.results_to_host(r1, s1)
+    pool = ood.KeyPool(n, "cuda", histograms=False)
+    # fill the pool through the rank path (keys only), then rank the pooled keys
+    ood.eval_segments(c, 1, n, gt=g, out_labels=(13,), method="rank", pos_capacity=32768, pool=pool)
+    r2, s2 = pool.evaluate(recall_level, method="rank")
+    v2, c2 = ood.results_to_host(r2.clone(), s2[:, :3])
+    return v1[0], c1[0], v2[0], c2[0]
+
+
+@pytest.mark.parametrize("n,pos_frac,quant", [(5000, 0.02, 0), (4099, 0.3, 50), (300001, 0.01, 0), (2000000, 0.02, 0),
+                                              (3000000, 0.4, 0), (1000003, 0.05, 1000)])
+def test_pooled_rank_equals_sort_and_oracle(n, pos_frac, quant):
+    rng = np.random.default_rng(n)
+    conf = rng.random(n).astype(np.float32)
+    if quant:
+        conf = (np.round(conf * quant) / quant).astype(np.float32)
+    conf[rng.random(n) < 0.07] = 1.0                                   # clamp plateau
+    gt = np.full(n, 2, np.int64)
+    gt[rng.random(n) < pos_frac] = 13
+    v1, c1, v2, c2 = _pooled_both(conf, gt)
+    assert v2[0] == v1[0] and v2[2] == v1[2] and abs(v2[1] - v1[1]) <= 1e-13
+    assert c2[0] == c1[0] and c2[1] == c1[1]
+    if n <= 400000:
+        np.testing.assert_allclose(v2, O.eval_ood_measure(conf, gt, (13,)), atol=1e-12)
+
+
+def test_pooled_rank_degenerate_and_levels():
+    from dml_b200 import ood
+    n = 100000
+    rng = np.random.default_rng(4)
+    base = rng.random(n).astype(np.float32)
+    cases = []
+    gt = np.zeros(n, np.int64); gt[:500] = 13
+    cases.append((np.full(n, 0.25, np.float32), gt.copy()))                                  # everything tied
+    cases.append((np.sort(base), gt.copy()))                                                 # positives = the lowest conf
+    cases.append((np.sort(base)[::-1].copy(), gt.copy()))                                    # positives = the highest conf
+    g2 = np.zeros(n, np.int64); g2[777] = 13
+    cases.append((base.copy(), g2))                                                          # one positive
+    g3 = np.full(n, 13, np.int64); g3[123] = 0
+    cases.append((base.copy(), g3))                                                          # one negative
+    for level in (0.95, 0.5, 1.0):
+        for conf, gt in cases:
+            v1, c1, v2, c2 = _pooled_both(conf, gt, level)
+            assert v2[0] == v1[0] and v2[2] == v1[2] and abs(v2[1] - v1[1]) <= 1e-13
+            np.testing.assert_allclose(v2, O.get_measures(-conf[gt == 13], -conf[gt != 13], recall_level=level), atol=1e-12)
+    # single class -> NaN row
+    c = torch.from_numpy(base).cuda()
+    pool = ood.KeyPool(n, "cuda", histograms=False)
+    ood.eval_segments(c, 1, n, gt=torch.zeros(n, dtype=torch.int64, device="cuda"), out_labels=(13,), method="rank", pool=pool)
+    r, s = pool.evaluate(method="rank")
+    assert np.isnan(r.cpu().numpy()[0, :3]).all()
+
+
+def test_key_pool_rank_over_batches_equals_sort():
+    """per-image batches through the rank path feed one pool; its pooled metric (rank) equals the sort path's"""
+    from dml_b200 import ood
+    rng = np.random.default_rng(12)
+    seg_len, batches = 30000, [3, 2, 4]
+    tot = sum(batches) * seg_len
+    pools = {m: ood.KeyPool(tot, "cuda") for m in ("sort", "rank")}
+    for b in batches:
+        conf = rng.random((b, seg_len)).astype(np.float32)
+        gt = np.where(rng.random((b, seg_len)) < 0.03, 13, 1).astype(np.uint8)
+        for m in ("sort", "rank"):
+            ood.eval_segments(torch.from_numpy(conf).cuda(), b, seg_len, gt=torch.from_numpy(gt).cuda(), out_labels=(13,),
+                              method=m, pool=pools[m])
+    a, _ = ood.results_to_host(*pools["sort"].evaluate())
+    r, st = pools["rank"].evaluate(method="rank")
+    b_, _ = ood.results_to_host(r, st[:, :3])
+    assert a[0, 0] == b_[0, 0] and a[0, 2] == b_[0, 2] and abs(a[0, 1] - b_[0, 1]) <= 1e-13
+    # a rank-filled pool evaluated by the sort path (no digit histograms were left: the sort counts them itself)
+    c, _ = ood.results_to_host(*pools["rank"].evaluate(method="sort"))
+    np.testing.assert_array_equal(a[:, [0, 2]], c[:, [0, 2]])
