@@ -64,14 +64,27 @@ __global__ void __launch_bounds__(256) pos_gather_kernel(const float* __restrict
   const bool vec_ok = bytes && (seg_len % PER == 0) && ((reinterpret_cast<uintptr_t>(gb) & 15) == 0);
   const long long nstep = (seg_len + PER - 1) / PER;
   const long long stride = (long long)gridDim.x * blockDim.x;
-  const long long q_end = ((nstep + stride - 1) / stride) * stride;   // block-uniform trip count (warp collectives below)
+  constexpr int U = 4;      // label loads in flight per thread (the loop is otherwise one memory latency per step:
+                            // the warp votes on the loaded labels before it moves on)
+  const long long q_end = ((nstep + U * stride - 1) / (U * stride)) * (U * stride);   // block-uniform trip count (warp collectives below)
   uint32_t* out = plist + (size_t)seg * cap;
-  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < q_end; q += stride) {
+  for (long long q0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; q0 < q_end; q0 += U * stride) {
+   uint4 wl[U];
+   if (vec_ok) {
+#pragma unroll
+     for (int u = 0; u < U; ++u) {
+       const long long q = q0 + u * stride;
+       wl[u] = q < nstep ? *reinterpret_cast<const uint4*>(gb + base + q * PER) : make_uint4(0u, 0u, 0u, 0u);
+     }
+   }
+#pragma unroll
+   for (int u = 0; u < U; ++u) {
+    const long long q = q0 + u * stride;
     unsigned flags = 0u;
     const long long p0 = q * PER;
     if (q < nstep) {
       if (vec_ok) {
-        const uint4 w = *reinterpret_cast<const uint4*>(gb + base + p0);
+        const uint4 w = wl[u];
         const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
         for (int j = 0; j < 4; ++j) flags |= byte_mask_to_bits(positive_bytes(ww[j], out_mask, pos_u8 != nullptr)) << (4 * j);
@@ -118,6 +131,7 @@ __global__ void __launch_bounds__(256) pos_gather_kernel(const float* __restrict
         ++dst;
       }
     }
+   }
   }
 }
 
@@ -368,7 +382,8 @@ __global__ void __launch_bounds__(RANK_THREADS, 1) rank_kernel(const float* __re
           for (int j = 0; j < VEC; ++j) {
             mn[j] = apply_norm(nmm, m[j]);
             // NumPy: c = 1 / (1 + exp(lamda * (e - thre))); mix = c*e + (1-c)*mmsp   (float32)
-            const float c = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(__fmul_rn(fz.lambda, __fsub_rn(v[j], fz.thr)))));
+            // (1 / x correctly rounded == IEEE 1.0f / x: the reciprocal sequence is half the division subroutine)
+            const float c = __frcp_rn(__fadd_rn(1.0f, expf(__fmul_rn(fz.lambda, __fsub_rn(v[j], fz.thr)))));
             mx[j] = __fadd_rn(__fmul_rn(c, v[j]), __fmul_rn(__fsub_rn(1.0f, c), mn[j]));
           }
           if constexpr (VEC == 4) {
@@ -382,6 +397,8 @@ __global__ void __launch_bounds__(RANK_THREADS, 1) rank_kernel(const float* __re
       }
       if (gn == 0) continue;
       // ---- negatives: lower bound among this pass's positive scores, one counter per (interval | tie) ---------
+      // (a register-counted short cut for keys above every positive was measured and dropped: the extra branch cost
+      //  more than the searches it saved -- most negatives of an image are NOT above its largest positive score)
       int lo[VEC], hi[VEC];
       uint32_t sk[VEC];
       bool act[VEC];
