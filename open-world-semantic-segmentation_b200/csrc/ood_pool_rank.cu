@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(256) pos_compact_kernel(const uint32_t* __rest
 
 // ---- distinct values of a sorted array ---------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) uniq_count_kernel(const uint32_t* __restrict__ a, long long n, uint32_t* __restrict__ bc) {
-  __shared__ uint32_t s_w[32];
+  __shared__ uint32_t s_w[33];
   const long long base = (long long)blockIdx.x * UNIQ_TILE + (long long)threadIdx.x * 4;
   uint32_t heads = 0;
 #pragma unroll
@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(1024) scan_u32_kernel(uint32_t* __restrict__ v
 
 __global__ void __launch_bounds__(1024) uniq_write_kernel(const uint32_t* __restrict__ a, long long n, const uint32_t* __restrict__ bc,
                                                           uint32_t* __restrict__ S, uint32_t* __restrict__ start) {
-  __shared__ uint32_t s_w[32];
+  __shared__ uint32_t s_w[33];
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const long long base = (long long)blockIdx.x * UNIQ_TILE + (long long)tid * 4;
   uint32_t k[4];
@@ -221,7 +221,7 @@ __global__ void __launch_bounds__(RANK_THREADS) bucket_count_kernel(const uint32
 // entries [t * PR_PER, (t + 1) * PR_PER)); returns the total
 constexpr int PR_PER = PR_MAX_BUCKETS / RANK_THREADS;
 template <int PER>
-__device__ __forceinline__ uint32_t block_excl_scan(uint32_t (&v)[PER], uint32_t* s_w /*[32]*/) {
+__device__ __forceinline__ uint32_t block_excl_scan(uint32_t (&v)[PER], uint32_t* s_w /*[33]*/) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int nw = (int)(blockDim.x >> 5);
   uint32_t sum = 0;
@@ -236,8 +236,21 @@ __device__ __forceinline__ uint32_t block_excl_scan(uint32_t (&v)[PER], uint32_t
   __syncthreads();              // s_w may still be read from a previous call
   if (lane == 31) s_w[w] = incl;
   __syncthreads();
-  uint32_t run = incl - sum, tot = 0;
-  for (int i = 0; i < nw; ++i) { if (i < w) run += s_w[i]; tot += s_w[i]; }
+  // second level: warp 0 scans the (<= 32) warp totals in place -> s_w[i] = exclusive prefix, s_w[32] = grand total
+  if (w == 0) {
+    const uint32_t t = lane < nw ? s_w[lane] : 0u;
+    uint32_t it = t;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t u = __shfl_up_sync(0xffffffffu, it, o);
+      if (lane >= o) it += u;
+    }
+    s_w[lane] = it - t;
+    if (lane == 31) s_w[32] = it;
+  }
+  __syncthreads();
+  uint32_t run = incl - sum + s_w[w];
+  const uint32_t tot = s_w[32];
 #pragma unroll
   for (int j = 0; j < PER; ++j) { const uint32_t c = v[j]; v[j] = run; run += c; }
   return tot;
@@ -245,7 +258,7 @@ __device__ __forceinline__ uint32_t block_excl_scan(uint32_t (&v)[PER], uint32_t
 
 __global__ void __launch_bounds__(RANK_THREADS) slice_prefix_kernel(const uint32_t* __restrict__ cnt, int B, uint32_t* __restrict__ rel,
                                                                     uint32_t* __restrict__ tot) {
-  __shared__ uint32_t s_w[32];
+  __shared__ uint32_t s_w[33];
   const uint32_t* c = cnt + (size_t)blockIdx.x * B;
   uint32_t v[PR_PER];
 #pragma unroll
@@ -261,7 +274,7 @@ __global__ void __launch_bounds__(RANK_THREADS) bucket_plan_kernel(const uint32_
                                                                    int n_slices, int B, uint32_t* __restrict__ sbase,
                                                                    Unit* __restrict__ units, uint32_t* __restrict__ n_units,
                                                                    long long unit_len) {
-  __shared__ uint32_t s_w[32];
+  __shared__ uint32_t s_w[33];
   const int tid = threadIdx.x;
   // (1) slice bases (n_slices <= PR_MAX_BUCKETS: PR_PER per thread)
   {
@@ -323,7 +336,7 @@ __global__ void __launch_bounds__(PT_THREADS, 2) bucket_scatter_kernel(const uin
   uint32_t* s_lut = s_delta + B;                                     // [RANK_LUT]
   uint32_t* s_stage = s_lut + RANK_LUT;                              // [PT_TILE] keys grouped by bucket
   unsigned short* s_sb = reinterpret_cast<unsigned short*>(s_stage + PT_TILE);   // [PT_TILE] their buckets
-  __shared__ uint32_t s_w[32];
+  __shared__ uint32_t s_w[33];
   const int tid = threadIdx.x;
   const uint32_t base = sbase[blockIdx.x];
   for (int i = tid; i < B; i += PT_THREADS) {
@@ -431,17 +444,17 @@ __global__ void __launch_bounds__(RANK_THREADS, 1) unit_rank_kernel(const uint32
     const uint32_t* p = p0 + head;
     const uint32_t len = len_all - head;
     const uint32_t nvec = len / 4;
-    for (uint32_t q = t; q < nvec; q += nthr) {
-      const uint4 v = *reinterpret_cast<const uint4*>(p + (size_t)q * 4);
-      const uint32_t sk[4] = {v.x >> 1, v.y >> 1, v.z >> 1, v.w >> 1};
-      int lo[4], hi[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) tab.range(sk[j], lo[j], hi[j]);
+    // 4 independent 16-byte loads in flight per thread (one CTA per SM: the loop is otherwise latency-bound)
+    for (uint32_t q = t; q < nvec; q += 4 * nthr) {
+      uint4 v[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const int l = tab.finish(sk[j], lo[j], hi[j]);
-        const bool eq = l < gn && s_S[l] == sk[j];
-        atomicAdd(&s_cnt[2 * l + (eq ? 1 : 0)], 1u);
+        const uint32_t qq = q + j * nthr;
+        v[j] = qq < nvec ? *reinterpret_cast<const uint4*>(p + (size_t)qq * 4) : make_uint4(0u, 0u, 0u, 0u);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (q + j * nthr < nvec) { rank_one(v[j].x); rank_one(v[j].y); rank_one(v[j].z); rank_one(v[j].w); }
       }
     }
     for (uint32_t i = nvec * 4 + t; i < len; i += nthr) rank_one(p[i]);

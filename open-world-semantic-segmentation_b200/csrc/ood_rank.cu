@@ -611,7 +611,8 @@ int dml_ood_rank_segments(const float* values, const float* minmax, int32_t minm
   // 1. positives
   if (seg_len > 0) {
     long long bx = (seg_len / 16 + 255) / 256;
-    const long long capb = n_seg >= 148 * 4 ? 4 : (148 * 8) / n_seg + 1;
+    // one resident wave (4 CTAs of 256 threads per SM): a partial second wave would cost a whole wave's time
+    const long long capb = n_seg >= 148 * 4 ? 1 : (148 * 4) / n_seg;
     if (bx > capb) bx = capb;
     if (bx < 1) bx = 1;
     dim3 grid((unsigned)bx, (unsigned)n_seg);
