@@ -23,10 +23,17 @@ def _ws(dev):
 
 
 def _to_cuda_f32(a) -> torch.Tensor:
+    """Scores are RANKED IN FLOAT32 (the reference's conf maps are float32; sklearn ranks whatever dtype it is given).
+    A float64 input whose distinct values collapse in float32 can gain ties the reference does not see: a lossy cast
+    is reported with a warning instead of silently changing the ranking."""
     if isinstance(a, torch.Tensor):
         t = a
     else:
         t = torch.from_numpy(np.ascontiguousarray(np.asarray(a)))
+    if t.dtype == torch.float64 and t.numel() and not torch.equal(t.to(torch.float32).to(torch.float64), t):
+        import warnings
+        warnings.warn("float64 scores are ranked as float32 keys on the GPU: values that differ only beyond float32 precision "
+                      "become ties (the reference ranks the float64 values)", RuntimeWarning, stacklevel=3)
     if not t.is_cuda:
         if not torch.cuda.is_available():
             ood.require_cuda(t, "scores")  # raises: there is no CPU fallback

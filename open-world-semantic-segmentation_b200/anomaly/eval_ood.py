@@ -83,6 +83,28 @@ def multiscale_score_map(z_list, segSize, mode: str = "dissum", exclude_back: bo
     return out.label, {"dissum": eds_n, "mmsp": msp_n, "mix": mix}[mode]
 
 
+def evaluate_image(segmentation_module, batch_data, cfg, reciprocal_average: bool = False):
+    """One image of the reference's ``evaluate()`` loop (anomaly/eval_ood_traditional.py:183-218,276-305,434-450) on the
+    fused path, with the reference's own objects: ``segmentation_module`` (``.encoder(img, return_feature_maps=True)``,
+    ``.decoder`` = this repo's ``PPMDeepsup_embedding``), ``batch_data`` (the loader item: ``img_data`` = list of
+    resized images, ``seg_label``) and ``cfg`` (``OOD.ood``, ``OOD.exclude_back``).  Per scale only the stride-8 logits
+    are produced (``decoder.forward_lowres``: final 1x1 conv fused into the distance head); ONE kernel then upsamples,
+    averages and scores -- the ten full-resolution ``F.interpolate`` / accumulate passes of the reference loop never run.
+    Returns ``(pred [H,W] int64, conf [H,W] fp32)`` device tensors, i.e. what :218 / :450 hand to the metric code."""
+    seg = batch_data["seg_label"][0]
+    seg_size = (int(seg.shape[0]), int(seg.shape[1]))
+    dev = next(segmentation_module.parameters()).device
+    z_list = []
+    with torch.no_grad():
+        for img in batch_data["img_data"]:
+            conv_out = segmentation_module.encoder(img.to(dev, non_blocking=True), return_feature_maps=True)
+            z, _ = segmentation_module.decoder.forward_lowres(conv_out)
+            z_list.append(z)
+        pred, conf = multiscale_score_map(z_list, seg_size, cfg.OOD.ood, cfg.OOD.exclude_back,
+                                          reciprocal_average=reciprocal_average)
+    return pred[0], conf[0]
+
+
 def eval_ood_measure(conf, seg_label, cfg, mask=None):
     """anomaly/eval_ood_traditional.py:128-148 (``cfg.OOD.out_labels``; ``mask`` filters the labels
     only -- like the reference, ``conf`` must then already be masked)."""

@@ -56,9 +56,21 @@ class CrossEntropyLoss(nn.Module):
         self.size_average = size_average
         self.shipped_early_return = shipped_early_return
 
+    def _ce_over_n(self, logit, target):
+        """``nn.CrossEntropyLoss(ignore_index, size_average)(logit, target) / n`` (utils/loss.py:39-42): the kernel
+        averages over the valid pixels; ``size_average=False`` (a sum in the reference) is that mean times the valid count,
+        taken from the same kernel's float64 parts vector."""
+        if self.size_average:
+            return dml_loss(logit, target, alpha=0.0, beta=0.0, ignore_index=self.ignore_index, input_is_logits=True)
+        loss, parts = dml_loss(logit, target, alpha=0.0, beta=0.0, ignore_index=self.ignore_index, input_is_logits=True,
+                               return_parts=True)
+        return loss * parts[4].to(loss.dtype)
+
     def forward(self, logit, target, features_in=None):
         if self.shipped_early_return:
-            return dml_loss(logit, target, alpha=0.0, beta=0.0, ignore_index=self.ignore_index, input_is_logits=True)
+            return self._ce_over_n(logit, target)
+        if not self.size_average:
+            raise NotImplementedError("size_average=False is only defined for the shipped CE / n form")
         loss = dml_loss(logit, target, alpha=self.alpha, beta=self.beta, ignore_index=self.ignore_index,
                         input_is_logits=True)
         if self.gamma != 0 and features_in is not None:
@@ -81,7 +93,7 @@ class CrossEntropyLoss_dis(nn.Module):
 
     def forward(self, logit, target, features_1=None, features_2=None):
         n = logit.shape[0]
-        ce_n = dml_loss(logit, target, alpha=0.0, beta=0.0, ignore_index=self.ignore_index, input_is_logits=True)
+        ce_n = CrossEntropyLoss._ce_over_n(self, logit, target)
         if self.shipped_early_return:
             return ce_n
         pad = torch.zeros(*features_1.shape[:3], 1, device=features_1.device, dtype=features_1.dtype)

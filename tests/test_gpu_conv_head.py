@@ -49,3 +49,42 @@ def test_ppm_decoder_lowres_uses_the_fused_conv_head():
     np.testing.assert_allclose(emb.cpu().numpy(), emb_ref.cpu().numpy(), rtol=1e-4, atol=1e-5)
     z_ref = O.distance_logits(emb_ref.cpu(), O.make_centers(13))
     np.testing.assert_allclose(z.cpu().numpy(), z_ref.numpy(), rtol=1e-4, atol=1e-4)
+
+
+def test_evaluate_image_fused_equals_the_reference_loop():
+    """anomaly.eval_ood.evaluate_image (stride-8 logits per scale + ONE fused upsample / average / score kernel) against
+    the reference's loop replayed with the same modules: forward(segSize) per scale, scores += ./n, score lines."""
+    from types import SimpleNamespace
+    from dml_b200.anomaly.eval_ood import evaluate_image, score_map
+    from dml_b200.anomaly.models import PPMDeepsup_embedding
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.manual_seed(1)
+
+    class Enc(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.c4 = nn.Conv2d(3, 32, 3, stride=8, padding=1)
+            self.c5 = nn.Conv2d(3, 64, 3, stride=8, padding=1)
+
+        def forward(self, x, return_feature_maps=False):
+            return [self.c4(x), self.c5(x)]
+
+    dec = PPMDeepsup_embedding(num_class=13, fc_dim=64, use_softmax=True)
+    with torch.no_grad():
+        dec.conv_last[4].weight.mul_(3.0)
+    module = SimpleNamespace(encoder=Enc().cuda().eval(), decoder=dec.cuda().eval(),
+                             parameters=lambda: iter(dec.parameters()))
+    H, W = 96, 160
+    imgs = [torch.randn(1, 3, h, w) for (h, w) in [(40, 72), (56, 96), (72, 120)]]
+    batch = {"img_data": imgs, "seg_label": torch.zeros(1, H, W, dtype=torch.long)}
+    cfg = SimpleNamespace(OOD=SimpleNamespace(ood="dissum", exclude_back=False))
+    pred, conf = evaluate_image(module, batch, cfg)
+    with torch.no_grad():
+        scores = torch.zeros(1, 13, H, W, device="cuda")
+        for img in imgs:
+            s_tmp, _ = module.decoder(module.encoder(img.cuda(), return_feature_maps=True), segSize=(H, W))
+            scores = scores + s_tmp / len(imgs)
+        pred_ref, conf_ref = score_map(scores, "dissum", False)
+    assert (pred.cpu() != pred_ref[0].cpu()).float().mean() < 1e-3
+    np.testing.assert_allclose(conf.cpu().numpy(), conf_ref[0].cpu().numpy(), rtol=1e-4, atol=1e-4)

@@ -247,3 +247,33 @@ def test_key_pool_rank_over_batches_equals_sort():
     # a rank-filled pool evaluated by the sort path (no digit histograms were left: the sort counts them itself)
     c, _ = ood.results_to_host(*pools["rank"].evaluate(method="sort"))
     np.testing.assert_array_equal(a[:, [0, 2]], c[:, [0, 2]])
+
+
+def test_rank_error_behaviour_and_plain_scores():
+    """NaN scores raise like scikit-learn in the reference path; plain scores of either sign (score_kind=1, key window
+    chosen from the data) rank like the sort path."""
+    from dml_b200 import ood
+    rng = np.random.default_rng(2)
+    n = 20000
+    conf = rng.random(n).astype(np.float32)
+    gt = np.where(rng.random(n) < 0.05, 13, 0).astype(np.int64)
+    bad = conf.copy()
+    bad[77] = np.nan
+    res, stats = ood.eval_segments(torch.from_numpy(bad).cuda(), 1, n, gt=torch.from_numpy(gt).cuda(), out_labels=(13,), method="rank")
+    with pytest.raises(ValueError, match="NaN"):
+        ood.results_to_host(res, stats)
+    # maxlogit-like scores: negative, higher = more positive
+    score = (-(rng.random(n) * 300 + 5)).astype(np.float32)
+    score[gt == 13] += 40
+    st = torch.empty(4, dtype=torch.int64, device="cuda")
+    from dml_b200._lib import check, lib, ptr, stream_ptr
+    s = torch.from_numpy(score).cuda()
+    check(lib().dml_ood_keystats(ptr(s), 1, 1, n, ptr(st), stream_ptr(s.device)), "dml_ood_keystats")
+    kmin = int(st[0].item())
+    pos = torch.from_numpy(gt == 13).cuda()
+    out = {}
+    for m in ("sort", "rank"):
+        r, t = ood.eval_segments(s, 1, n, positive=pos, score_kind=1, key_base=kmin, method=m)
+        out[m], _ = ood.results_to_host(r, t)
+    assert out["rank"][0, 0] == out["sort"][0, 0] and out["rank"][0, 2] == out["sort"][0, 2]
+    np.testing.assert_allclose(out["rank"][0], O.get_measures(score[gt == 13], score[gt != 13]), atol=1e-12)
