@@ -14,6 +14,7 @@
 // The counters are plain sums over the negatives, so a multi-GPU evaluation needs no exchange of the negatives at
 // all: every rank ranks ITS negatives against the all-gathered positives and the counters are all-reduced
 // (distributed.pooled_measures(mode="rank")).  Reference semantics: anomaly/anom_utils.py:25-78 over all pixels.
+#include <cstdlib>
 #include "ood_rank.cuh"
 
 namespace dml {
@@ -21,7 +22,11 @@ namespace {
 
 constexpr int PR_PASS_CAP = 12288;        // positive groups per bucket (shared memory: 48 KB keys + 96 KB counters + 16 KB LUT)
 constexpr int PR_MAX_BUCKETS = 4096;
-constexpr long long PR_UNIT = 1ll << 20;  // keys per ranking unit
+constexpr long long PR_FLAT_BELOW = 1200;  // mean chunk length below which unit_rank walks its chunks as one flat sequence (A/B on
+                                          // the B200, profiles/r2u_unit_rank_ab.txt: 787 -> 2.12 vs 2.36 ms, 1570 -> 3.82 vs 3.75, 6300 -> 13.9 vs 12.9)
+constexpr int PR_MAX_SLICES = 148 * 2;    // slices of the key array: one per CTA of the counting / scatter passes, 2 CTAs per SM
+constexpr long long PR_UNIT = 1ll << 20;  // keys per ranking unit, at most (and at least 1 / (8 * 148) of the keys, >= 64 K:
+                                          // a 1/8 shard cut into 1 M-key units left 165 long units for 148 SMs -- two waves)
 constexpr int UNIQ_TILE = 4096;
 constexpr int SCAN_GROUPS_PER_BLOCK = 8192;
 
@@ -269,6 +274,7 @@ __global__ void __launch_bounds__(RANK_THREADS) slice_prefix_kernel(const uint32
   if (threadIdx.x == 0) tot[blockIdx.x] = t;
 }
 
+constexpr int PLAN_MLP = 16;
 // slice bases + ranking units (single CTA).  A unit = bucket b, slices [s0, s1): consecutive slices until ~unit_len keys.
 __global__ void __launch_bounds__(RANK_THREADS) bucket_plan_kernel(const uint32_t* __restrict__ cnt, const uint32_t* __restrict__ tot,
                                                                    int n_slices, int B, uint32_t* __restrict__ sbase,
@@ -285,42 +291,55 @@ __global__ void __launch_bounds__(RANK_THREADS) bucket_plan_kernel(const uint32_
 #pragma unroll
     for (int j = 0; j < PR_PER; ++j) { const int sidx = tid * PR_PER + j; if (sidx < n_slices) sbase[sidx] = v[j]; }
   }
-  // (2) units per bucket: count, scan, emit
-  uint32_t nu[PR_PER];
+  // (2) units per bucket: count, scan, emit.  Bucket b = tid + 1024 j in the two walks over the slices (every thread busy for
+  // B <= 1024), blocked ownership only for the scan in between.
+  __shared__ uint32_t s_nu[PR_MAX_BUCKETS], s_ub[PR_MAX_BUCKETS];
+  // PLAN_MLP independent loads in flight: one dependent L2 round trip per slice made this single CTA 0.25 ms
+  for (int b = tid; b < B; b += RANK_THREADS) {
+    unsigned long long acc = 0;
+    uint32_t nub = 0u;
+    for (int sb = 0; sb < n_slices; sb += PLAN_MLP) {
+      uint32_t c[PLAN_MLP];
 #pragma unroll
-  for (int j = 0; j < PR_PER; ++j) {
-    const int b = tid * PR_PER + j;
-    nu[j] = 0u;
-    if (b < B) {
-      unsigned long long acc = 0;
-      for (int sidx = 0; sidx < n_slices; ++sidx) {
-        acc += cnt[(size_t)sidx * B + b];
-        if (acc >= (unsigned long long)unit_len) { ++nu[j]; acc = 0; }
+      for (int q = 0; q < PLAN_MLP; ++q) c[q] = sb + q < n_slices ? cnt[(size_t)(sb + q) * B + b] : 0u;
+#pragma unroll
+      for (int q = 0; q < PLAN_MLP; ++q) {
+        acc += c[q];
+        if (acc >= (unsigned long long)unit_len) { ++nub; acc = 0; }
       }
-      if (acc) ++nu[j];
     }
+    if (acc) ++nub;
+    s_nu[b] = nub;
   }
+  __syncthreads();
   uint32_t ub[PR_PER];
 #pragma unroll
-  for (int j = 0; j < PR_PER; ++j) ub[j] = nu[j];
+  for (int j = 0; j < PR_PER; ++j) { const int b = tid * PR_PER + j; ub[j] = b < B ? s_nu[b] : 0u; }
   const uint32_t total = block_excl_scan(ub, s_w);
   if (tid == 0) *n_units = total;
 #pragma unroll
-  for (int j = 0; j < PR_PER; ++j) {
-    const int b = tid * PR_PER + j;
-    if (b < B && nu[j]) {
-      uint32_t u = ub[j];
-      unsigned long long acc = 0;
-      int s0 = 0;
-      for (int sidx = 0; sidx < n_slices; ++sidx) {
-        acc += cnt[(size_t)sidx * B + b];
-        if (acc >= (unsigned long long)unit_len) {
+  for (int j = 0; j < PR_PER; ++j) { const int b = tid * PR_PER + j; if (b < B) s_ub[b] = ub[j]; }
+  __syncthreads();
+  for (int b = tid; b < B; b += RANK_THREADS) {
+    if (!s_nu[b]) continue;
+    uint32_t u = s_ub[b];
+    unsigned long long acc = 0;
+    int s0 = 0;
+    for (int sb = 0; sb < n_slices; sb += PLAN_MLP) {
+      uint32_t c[PLAN_MLP];
+#pragma unroll
+      for (int q = 0; q < PLAN_MLP; ++q) c[q] = sb + q < n_slices ? cnt[(size_t)(sb + q) * B + b] : 0u;
+#pragma unroll
+      for (int q = 0; q < PLAN_MLP; ++q) {
+        const int sidx = sb + q;
+        acc += c[q];
+        if (acc >= (unsigned long long)unit_len) {       // (padding entries add 0 to acc = 0 or to acc < unit_len)
           units[u++] = Unit{(uint32_t)b, (uint32_t)s0, (uint32_t)(sidx + 1), 0u};
           s0 = sidx + 1; acc = 0;
         }
       }
-      if (acc) units[u++] = Unit{(uint32_t)b, (uint32_t)s0, (uint32_t)n_slices, 0u};
     }
+    if (acc) units[u++] = Unit{(uint32_t)b, (uint32_t)s0, (uint32_t)n_slices, 0u};
   }
 }
 
@@ -406,6 +425,7 @@ __global__ void __launch_bounds__(PT_THREADS, 2) bucket_scatter_kernel(const uin
 
 // one unit = the chunks (slice s, bucket b), s in [s0, s1), of one bucket: ~PR_UNIT grouped negatives, ranked against
 // the bucket's positive groups in shared memory
+template <bool FLAT>
 __global__ void __launch_bounds__(RANK_THREADS, 1) unit_rank_kernel(const uint32_t* __restrict__ part, const Unit* __restrict__ units,
                                                                     const uint32_t* __restrict__ n_units, const uint32_t* __restrict__ cntt,
                                                                     const uint32_t* __restrict__ rel, const uint32_t* __restrict__ sbase,
@@ -420,11 +440,41 @@ __global__ void __launch_bounds__(RANK_THREADS, 1) unit_rank_kernel(const uint32
   uint32_t* s_cnt = s_S + cap_b;                                                // [2 cap_b + 2]
   uint32_t* s_lut = s_cnt + 2 * cap_b + 2;
   const int tid = threadIdx.x;
+  // The unit's chunks (slice, bucket) as ONE flat sequence of aligned 16-byte vectors: chunk j covers the vectors
+  // [coff >> 2, (coff + len + 3) >> 2) of `part` (elements outside [coff, coff + len) masked), s_vpre = exclusive prefix of
+  // the vector counts.  Every thread strides over the flat index, so the work is balanced whatever the chunk lengths are
+  // (the r2l form -- long chunks by the whole CTA, short ones one warp each -- spent 60 % of a 1/8 shard's time fetching
+  // descriptors one dependent L2 round trip at a time and at the final barrier behind the warp with the longest chunk).
+  __shared__ uint32_t s_clen[PR_MAX_SLICES], s_coff[PR_MAX_SLICES], s_vpre[PR_MAX_SLICES + 1];
+  const uint32_t n_ch = u.s1 - u.s0;
+  for (uint32_t j = tid; j < n_ch; j += RANK_THREADS) {
+    const size_t e = (size_t)(u.s0 + j) * B + u.bucket;
+    const uint32_t len = cntt[e], off = sbase[u.s0 + j] + rel[e];
+    s_clen[j] = len;
+    s_coff[j] = off;
+    s_vpre[j + 1] = len ? ((off + len + 3u) >> 2) - (off >> 2) : 0u;
+  }
   for (int i = tid; i < gn; i += RANK_THREADS) s_S[i] = S[g0 + i];
   for (int i = tid; i < 2 * gn + 2; i += RANK_THREADS) s_cnt[i] = 0u;
   __syncthreads();
+  if (tid < 32) {                                   // warp 0: inclusive scan of the vector counts, 32 at a time
+    uint32_t carry = 0u;
+    for (uint32_t b0 = 0; b0 < n_ch; b0 += 32) {
+      const uint32_t j = b0 + tid;
+      uint32_t v = j < n_ch ? s_vpre[j + 1] : 0u;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, v, o);
+        if (tid >= o) v += t;
+      }
+      v += carry;
+      if (j < n_ch) s_vpre[j + 1] = v;
+      carry = __shfl_sync(0xffffffffu, v, 31);
+    }
+    if (tid == 0) s_vpre[0] = 0u;
+  }
   SmemTable tab;
-  tab.build(s_S, s_lut, gn, key_base);
+  tab.build(s_S, s_lut, gn, key_base);              // (barriers inside: s_vpre is complete behind them)
   auto rank_one = [&](uint32_t key) {
     const uint32_t sk = key >> 1;
     int lo, hi;
@@ -433,42 +483,75 @@ __global__ void __launch_bounds__(RANK_THREADS, 1) unit_rank_kernel(const uint32
     const bool eq = l < gn && s_S[l] == sk;
     atomicAdd(&s_cnt[2 * l + (eq ? 1 : 0)], 1u);
   };
-  // A chunk is ranked by `nthr` consecutive threads starting at thread `t0`-relative index `t`: long chunks (the buckets
-  // where positives are sparse hold most of the negatives: millions of keys per chunk) by the whole CTA, short ones
-  // (a few thousand keys) by one warp each, 32 chunks in flight per CTA.
-  auto rank_chunk = [&](const uint32_t* p0, uint32_t len_all, int t, int nthr) {
-    // scalar head up to the next 16-byte boundary, vector body, scalar tail
-    uint32_t head = (uint32_t)((16 - (reinterpret_cast<uintptr_t>(p0) & 15)) & 15) / 4;
-    if (head > len_all) head = len_all;
-    if (t < (int)head) rank_one(p0[t]);
-    const uint32_t* p = p0 + head;
-    const uint32_t len = len_all - head;
-    const uint32_t nvec = len / 4;
-    // 4 independent 16-byte loads in flight per thread (one CTA per SM: the loop is otherwise latency-bound)
-    for (uint32_t q = t; q < nvec; q += 4 * nthr) {
-      uint4 v[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const uint32_t qq = q + j * nthr;
-        v[j] = qq < nvec ? *reinterpret_cast<const uint4*>(p + (size_t)qq * 4) : make_uint4(0u, 0u, 0u, 0u);
+  if constexpr (FLAT) {
+    const uint32_t V = s_vpre[n_ch];
+    const uint4* pv = reinterpret_cast<const uint4*>(part);           // (the workspace is 256-byte aligned)
+    constexpr int U = 4;                                              // independent 16-byte loads in flight per thread
+    uint32_t j = 0;                                                   // chunk of the previous vector: the flat index only grows
+    for (uint32_t q0 = tid; q0 < V; q0 += U * RANK_THREADS) {
+      uint4 v[U];
+      uint32_t rel_e[U], len_e[U];
+  #pragma unroll
+      for (int k = 0; k < U; ++k) {
+        const uint32_t q = q0 + k * RANK_THREADS;
+        v[k] = make_uint4(0u, 0u, 0u, 0u);
+        rel_e[k] = 0u; len_e[k] = 0u;
+        if (q < V) {
+          if (q >= s_vpre[j + 1]) {                                   // first chunk with s_vpre[j + 1] > q
+            uint32_t lo = j + 1, hi = n_ch - 1;
+            while (lo < hi) {
+              const uint32_t mid = (lo + hi) >> 1;
+              if (s_vpre[mid + 1] > q) hi = mid; else lo = mid + 1;
+            }
+            j = lo;
+          }
+          const uint32_t off = s_coff[j];
+          const uint32_t vec = (off >> 2) + (q - s_vpre[j]);
+          v[k] = pv[vec];
+          rel_e[k] = vec * 4u - off;                                  // element c of the vector is chunk element rel_e + c (mod 2^32)
+          len_e[k] = s_clen[j];
+        }
       }
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        if (q + j * nthr < nvec) { rank_one(v[j].x); rank_one(v[j].y); rank_one(v[j].z); rank_one(v[j].w); }
+  #pragma unroll
+      for (int k = 0; k < U; ++k) {
+        if (rel_e[k] + 0u < len_e[k]) rank_one(v[k].x);
+        if (rel_e[k] + 1u < len_e[k]) rank_one(v[k].y);
+        if (rel_e[k] + 2u < len_e[k]) rank_one(v[k].z);
+        if (rel_e[k] + 3u < len_e[k]) rank_one(v[k].w);
       }
     }
-    for (uint32_t i = nvec * 4 + t; i < len; i += nthr) rank_one(p[i]);
-  };
-  constexpr uint32_t LONG_CHUNK = 32768;
-  for (uint32_t sl = u.s0; sl < u.s1; ++sl) {
-    const size_t e = (size_t)sl * B + u.bucket;
-    const uint32_t len_all = cntt[e];
-    if (len_all >= LONG_CHUNK) rank_chunk(part + sbase[sl] + rel[e], len_all, tid, RANK_THREADS);
-  }
-  for (uint32_t sl = u.s0 + (uint32_t)(tid >> 5); sl < u.s1; sl += RANK_THREADS / 32) {
-    const size_t e = (size_t)sl * B + u.bucket;
-    const uint32_t len_all = cntt[e];
-    if (len_all > 0u && len_all < LONG_CHUNK) rank_chunk(part + sbase[sl] + rel[e], len_all, tid & 31, 32);
+  } else {
+    // long chunks by the whole CTA, short ones one warp each (32 chunks in flight per CTA)
+    auto rank_chunk = [&](const uint32_t* p0, uint32_t len_all, int t, int nthr) {
+      uint32_t head = (uint32_t)((16 - (reinterpret_cast<uintptr_t>(p0) & 15)) & 15) / 4;
+      if (head > len_all) head = len_all;
+      if (t < (int)head) rank_one(p0[t]);
+      const uint32_t* p = p0 + head;
+      const uint32_t len = len_all - head;
+      const uint32_t nvec = len / 4;
+      for (uint32_t q = t; q < nvec; q += 4 * nthr) {
+        uint4 v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint32_t qq = q + k * nthr;
+          v[k] = qq < nvec ? *reinterpret_cast<const uint4*>(p + (size_t)qq * 4) : make_uint4(0u, 0u, 0u, 0u);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (q + k * nthr < nvec) { rank_one(v[k].x); rank_one(v[k].y); rank_one(v[k].z); rank_one(v[k].w); }
+        }
+      }
+      for (uint32_t i = nvec * 4 + t; i < len; i += nthr) rank_one(p[i]);
+    };
+    constexpr uint32_t LONG_CHUNK = 32768;
+    for (uint32_t j = 0; j < n_ch; ++j) {
+      const uint32_t len_all = s_clen[j];
+      if (len_all >= LONG_CHUNK) rank_chunk(part + s_coff[j], len_all, tid, RANK_THREADS);
+    }
+    for (uint32_t j = (uint32_t)(tid >> 5); j < n_ch; j += RANK_THREADS / 32) {
+      const uint32_t len_all = s_clen[j];
+      if (len_all > 0u && len_all < LONG_CHUNK) rank_chunk(part + s_coff[j], len_all, tid & 31, 32);
+    }
   }
   __syncthreads();
   unsigned long long* c = cnt + 2 * g0;
@@ -660,7 +743,7 @@ size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 struct BucketPlan {
   int B, n_slices;
   long long cap_b, slice_len;
-  long long max_units;
+  long long max_units, unit_len;
   size_t off_part, off_U, off_cnt, off_rel, off_tot, off_sbase, off_units, off_nunits, off_end;
 };
 // returns false when the positives have more distinct scores than PR_MAX_BUCKETS buckets can hold
@@ -670,10 +753,13 @@ bool make_bucket_plan(long long n, long long G, BucketPlan& p) {
   if (p.B > PR_MAX_BUCKETS) return false;
   p.cap_b = (G + p.B - 1) / p.B;
   if (p.cap_b < 1) p.cap_b = 1;
-  p.max_units = n / PR_UNIT + p.B + 1;
+  p.unit_len = n / (148 * 8);
+  if (p.unit_len > PR_UNIT) p.unit_len = PR_UNIT;
+  if (p.unit_len < 65536) p.unit_len = 65536;
+  p.max_units = n / p.unit_len + p.B + 1;
   // one slice per CTA of the counting / scatter passes: 2 CTAs per SM, at least 16384 keys each
   long long ns = (n + 16383) / 16384;
-  if (ns > 148 * 2) ns = 148 * 2;
+  if (ns > PR_MAX_SLICES) ns = PR_MAX_SLICES;
   if (ns < 1) ns = 1;
   p.n_slices = (int)ns;
   p.slice_len = (((n + ns - 1) / ns) + 3) & ~3ll;
@@ -775,14 +861,24 @@ int dml_ood_bucket_rank(const uint32_t* keys, int64_t n, const uint32_t* group_s
   DML_LAUNCH_CHECK();
   slice_prefix_kernel<<<(unsigned)p.n_slices, RANK_THREADS, 0, stream>>>(cntt, p.B, rel, tot);
   DML_LAUNCH_CHECK();
-  bucket_plan_kernel<<<1, RANK_THREADS, 0, stream>>>(cntt, tot, p.n_slices, p.B, sbase, units, n_units, PR_UNIT);
+  bucket_plan_kernel<<<1, RANK_THREADS, 0, stream>>>(cntt, tot, p.n_slices, p.B, sbase, units, n_units, p.unit_len);
   DML_LAUNCH_CHECK();
   bucket_scatter_kernel<<<(unsigned)p.n_slices, PT_THREADS, smem_s, stream>>>(keys, n, p.slice_len, U, p.B, key_base, rel, sbase, part);
   DML_LAUNCH_CHECK();
   const size_t smem_u = (size_t)p.cap_b * 4 + ((size_t)2 * p.cap_b + 2) * 4 + SmemTable::lut_bytes() + 16;
-  DML_CUDA_TRY(cudaFuncSetAttribute(unit_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_u));
-  unit_rank_kernel<<<(unsigned)p.max_units, RANK_THREADS, smem_u, stream>>>(part, units, n_units, cntt, rel, sbase, group_scores, n_groups,
-                                                                           p.cap_b, p.B, key_base, counters);
+  // chunk walk: flat (balanced for any chunk length) when the mean (slice, bucket) chunk is short, else long chunks by the
+  // CTA + short ones per warp; DML_UNIT_RANK=flat|chunk overrides (A/B runs)
+  bool flat = n / ((long long)p.n_slices * p.B) < PR_FLAT_BELOW;
+  if (const char* e = getenv("DML_UNIT_RANK")) flat = e[0] == 'f';
+  if (flat) {
+    DML_CUDA_TRY(cudaFuncSetAttribute(unit_rank_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_u));
+    unit_rank_kernel<true><<<(unsigned)p.max_units, RANK_THREADS, smem_u, stream>>>(part, units, n_units, cntt, rel, sbase, group_scores,
+                                                                                   n_groups, p.cap_b, p.B, key_base, counters);
+  } else {
+    DML_CUDA_TRY(cudaFuncSetAttribute(unit_rank_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_u));
+    unit_rank_kernel<false><<<(unsigned)p.max_units, RANK_THREADS, smem_u, stream>>>(part, units, n_units, cntt, rel, sbase, group_scores,
+                                                                                    n_groups, p.cap_b, p.B, key_base, counters);
+  }
   DML_LAUNCH_CHECK();
   return DML_OK;
 }
