@@ -54,6 +54,9 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-pooled", action="store_true")
+    ap.add_argument("--no-overlap-exchange", action="store_true",
+                    help="N > 1: exchange the positives after the per-image pass (count exchange + local sort + one bulk all-gather) "
+                         "instead of batch by batch behind it (A/B)")
     ap.add_argument("--no-extra", action="store_true", help="skip the bounded side measurements (roofline.extra, strong scaling, config 5, pooled self-check)")
     ap.add_argument("--config5-images", type=int, default=4000, help="total images of the metric scaling sweep (BASELINE.json configs[4]; N > 1 only, 0 = skip)")
     ap.add_argument("--pooled-keys", default=os.environ.get("DML_BENCH_POOLED_KEYS", "reuse"), choices=["reuse", "regenerate"],
@@ -349,6 +352,12 @@ class Pipeline:
         if not args.no_pooled and args.pooled_keys == "reuse":
             self.pool = ood.KeyPool(n * self.hw, device, workspace=self.ws_pool,
                                     histograms=(world == 1 and args.metric_method == "sort"))
+        # N > 1, minority-rank path: every batch ships its positives to all ranks while the following batches are evaluated
+        self.exchange = None
+        if self.pool is not None and world > 1 and args.metric_method == "rank" and not args.no_overlap_exchange:
+            from dml_b200 import distributed as D
+            self.exchange = D.PositiveExchange(device, self.chunk * ood.POS_CAPACITY_DEFAULT, len(self.bounds))
+            self.pool.exchange = self.exchange
         self.outs = []
         for (s, e) in self.bounds:
             self.outs.append(H.HeadOutput(label=self.label[s:e], eds=self.eds[s:e], msp=self.msp[s:e],
@@ -409,7 +418,8 @@ class Pipeline:
                 if rank_mode and self.pool.pos is not None:
                     ks = ks + (self.pool.pos, self.pool.pos_count)
             self.pooled_result = D.pooled_measures(self.conf.view(-1), gt_all.view(-1), (self.k,), workspace=self.ws_pool,
-                                                   timing=True, keys_and_stats=ks, mode="rank" if rank_mode else "partition")
+                                                   timing=True, keys_and_stats=ks, mode="rank" if rank_mode else "partition",
+                                                   exchange=self.exchange)
 
     def reduce_across_ranks(self):
         """the two small collectives of SURVEY.md section 8(e): the reference's aggregate (mean over ALL images of the
@@ -530,7 +540,7 @@ def extra_rooflines(device, peak):
     return out
 
 
-def verify_pooled(pipe, world, rank, images=4):
+def verify_pooled(pipe, world, rank, images=4, gt=None):
     """Driver-visible correctness of the pooled metric: the packed keys of the first `images` images of every rank are
     (a) evaluated by the path the timed step uses (single GPU: KeyPool / rank_keys; N > 1: the NCCL exchange) and
     (b) gathered on rank 0 and evaluated there as ONE segment by the single-GPU radix-sort path.  AUROC / FPR must be
@@ -549,6 +559,7 @@ def verify_pooled(pipe, world, rank, images=4):
     if world == 1 and not rank_mode:
         return {"verified": None, "note": "single GPU sort path is the reference itself"}
     ws = ood.OodWorkspace(pipe.device)
+    route = None
     if world == 1:
         if rank_mode:
             got = ood.rank_keys(keys, st.view(1, 4), recall_level=0.95, workspace=ws).cpu().numpy()[0, :3]
@@ -556,8 +567,24 @@ def verify_pooled(pipe, world, rank, images=4):
             got = None
         all_keys, tot = keys, st
     else:
-        a, p_, f, _ = D.pooled_measures(None, None, (pipe.k,), workspace=ws, keys_and_stats=(keys, st),
-                                        mode="rank" if rank_mode else "partition")
+        ex = None
+        if pipe.exchange is not None:
+            # the timed step's own route: the subset is evaluated again batch by batch (2 images each) on a small pool
+            # whose PositiveExchange ships the positives as they are found; its keys are the ones gathered below
+            mini = ood.KeyPool(nk, pipe.device, workspace=ood.OodWorkspace(pipe.device), histograms=False)
+            ex = D.PositiveExchange(pipe.device, 2 * ood.POS_CAPACITY_DEFAULT, (m + 1) // 2)
+            mini.exchange = ex
+            mini.reset()
+            wsi = ood.OodWorkspace(pipe.device)
+            for s0 in range(0, m, 2):
+                s1 = min(s0 + 2, m)
+                ood.eval_segments(pipe.eds[s0:s1], s1 - s0, pipe.hw, gt=gt[s0:s1], out_labels=(pipe.k,), score_kind=0,
+                                  minmax=pipe.minmax[s0:s1], minmax_slot=0, workspace=wsi, pool=mini, method="rank")
+            keys, st = mini.keys[:nk], mini.stats[0].clone()
+            st[3] = 0
+        a, p_, f, info = D.pooled_measures(None, None, (pipe.k,), workspace=ws, keys_and_stats=(keys, st),
+                                           mode="rank" if rank_mode else "partition", exchange=ex)
+        route = info.get("positives_from")
         got = np.array([a, p_, f])
         gathered = [torch.empty_like(keys) for _ in range(world)] if rank == 0 else None
         dist.gather(keys, gathered, dst=0)
@@ -579,6 +606,7 @@ def verify_pooled(pipe, world, rank, images=4):
     ok = bool(got[0] == ref[0] and got[2] == ref[2] and abs(got[1] - ref[1]) <= 1e-12)
     return {"verified": ok, "pairs": int(n_all), "images_per_rank": m, "d_auroc": float(got[0] - ref[0]),
             "d_aupr": float(got[1] - ref[1]), "d_fpr": float(got[2] - ref[2]),
+            "positives_from": route,
             "reference": "all ranks' keys gathered on rank 0, one segment, single-GPU radix sort + scan"}
 
 
@@ -629,6 +657,8 @@ def config5_run(args, device, rank, world, barrier, total_images, steps=2):
     gen = torch.Generator(device=device).manual_seed(5000 + rank)
     chunk = 37
     method = args.metric_method
+    # (no PositiveExchange here: the timed region is the pooled stage alone, so its all-gather of the positives must stay
+    #  inside it -- in the full step it hides behind the per-image pass)
     for s0 in range(0, m, chunk):
         nb = min(chunk, m - s0)
         x, gt = synth_chunk_torch(nb, k, h, w, gen, device)
@@ -887,7 +917,7 @@ def run_ours(args):
     pooled_check = extra = strong = config5 = None
     if not args.no_extra:
         if not args.no_pooled:
-            pooled_check = verify_pooled(pipe, world, rank)
+            pooled_check = verify_pooled(pipe, world, rank, gt=gt_all)
         if rank == 0 and world == 1:
             extra = extra_rooflines(device, peak)
         if world > 1:

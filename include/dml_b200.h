@@ -380,6 +380,14 @@ DML_API int dml_ood_rank_export_positives(const void* rank_workspace, size_t wor
  * The host reads *count and *n_unique between the calls (two small synchronisations per pooled evaluation). */
 DML_API int dml_ood_pos_compact(const uint32_t* keys, int64_t n, uint32_t* pos_keys_out, int64_t capacity, long long* count,
                         dml_stream_t stream);
+/* Concatenates the key lists of `n_slots` fixed-capacity slot records, in slot order, into `out` (device):
+ * record i starts at slots + i * stride_words (u32 words, 8-byte aligned, stride even); its words 0..1 hold the int64
+ * number of keys (clamped to [0, slot_capacity]), its keys start at word `hdr_words`.  The records are the per-batch
+ * positives' lists that the ranks all-gather while the per-image pass is still running (the reference has no
+ * counterpart: anomaly/eval_ood_traditional.py:128-148 evaluates image by image on one device); the host reads the
+ * headers once to size `out`.  Nothing is written when the lists exceed out_capacity. */
+DML_API int dml_ood_slots_gather(const uint32_t* slots, int32_t n_slots, int64_t stride_words, int32_t hdr_words,
+                         int64_t slot_capacity, uint32_t* out, int64_t out_capacity, dml_stream_t stream);
 DML_API size_t dml_ood_unique_workspace_bytes(int64_t n);
 DML_API int dml_ood_unique_counts(const uint32_t* sorted_keys, int64_t n, uint32_t* values_out, uint32_t* counts_out,
                           long long* n_unique, void* workspace, size_t workspace_bytes, dml_stream_t stream);

@@ -738,6 +738,33 @@ __global__ void __launch_bounds__(1024) pscan_final_kernel(const uint32_t* __res
   }
 }
 
+// Fixed-capacity slot records (header word 0..1 = int64 key count, keys from word `hdr`) -> one contiguous key list, in
+// slot order.  The records are what the ranks all-gather batch by batch while the per-image pass is still running
+// (distributed.PositiveExchange); grid (n_slots, SG_SPLIT).
+constexpr int SG_SPLIT = 8;
+__global__ void __launch_bounds__(256) slots_gather_kernel(const uint32_t* __restrict__ slots, int n_slots, long long stride, int hdr,
+                                                           long long cap, uint32_t* __restrict__ out, long long out_capacity) {
+  __shared__ unsigned long long s_part[8];
+  const int b = blockIdx.x;
+  auto count_of = [&](int i) -> unsigned long long {
+    const long long c = *reinterpret_cast<const long long*>(slots + (size_t)i * stride);
+    return (unsigned long long)(c < 0 ? 0 : (c > cap ? cap : c));
+  };
+  unsigned long long acc = 0;
+  for (int i = threadIdx.x; i < b; i += 256) acc += count_of(i);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  unsigned long long base = 0;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) base += s_part[w];
+  const unsigned long long cnt = count_of(b);
+  if (base + cnt > (unsigned long long)out_capacity) return;
+  const uint32_t* src = slots + (size_t)b * stride + hdr;
+  for (unsigned long long i = (unsigned long long)blockIdx.y * 256 + threadIdx.x; i < cnt; i += 256ull * SG_SPLIT) out[base + i] = src[i];
+}
+
 size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 struct BucketPlan {
@@ -793,6 +820,20 @@ int dml_ood_pos_compact(const uint32_t* keys, int64_t n, uint32_t* pos_keys_out,
   if (blocks > 148 * 16) blocks = 148 * 16;
   if (blocks < 1) blocks = 1;
   pos_compact_kernel<<<(unsigned)blocks, 256, 0, stream>>>(keys, n, pos_keys_out, capacity, (unsigned long long*)count);
+  DML_LAUNCH_CHECK();
+  return DML_OK;
+}
+
+int dml_ood_slots_gather(const uint32_t* slots, int32_t n_slots, int64_t stride_words, int32_t hdr_words, int64_t slot_capacity,
+                         uint32_t* out, int64_t out_capacity, dml_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (n_slots < 0 || n_slots > 65535 || hdr_words < 2 || slot_capacity < 0 || stride_words < hdr_words + slot_capacity ||
+      (stride_words & 1) || out_capacity < 0 || (n_slots > 0 && !slots) || (out_capacity > 0 && !out))
+    return DML_ERR_INVALID_ARG;
+  if ((reinterpret_cast<uintptr_t>(slots) & 7) != 0) return DML_ERR_INVALID_ARG;      // the int64 counts are read in place
+  if (n_slots == 0) return DML_OK;
+  slots_gather_kernel<<<dim3((unsigned)n_slots, SG_SPLIT), 256, 0, stream>>>(slots, n_slots, stride_words, hdr_words, slot_capacity, out,
+                                                                             out_capacity);
   DML_LAUNCH_CHECK();
   return DML_OK;
 }

@@ -137,6 +137,15 @@ class CudaOps:
     def empty_keys(self, n, tag):
         return self.ws.get("d_recv_" + tag, 4 * max(n, 1)).view(torch.int32)[:n]
 
+    def slots_gather(self, records, hdr_words, slot_keys, total):
+        """[n_records, stride] int32 slot records (``PositiveExchange``) -> their ``total`` keys, contiguous, in record order"""
+        from ._lib import check, lib, ptr, stream_ptr
+        out = self.empty_keys(total, "rk_all")
+        with torch.cuda.device(self.device):
+            check(lib().dml_ood_slots_gather(ptr(records), records.shape[0], records.shape[1], hdr_words, slot_keys, ptr(out),
+                                             total, stream_ptr(self.device)), "dml_ood_slots_gather")
+        return out
+
     def sample_unsorted(self, keys, n_samples):
         """strided sample of unsorted keys (int32 bit patterns; -1 marks an empty shard)"""
         n = keys.numel()
@@ -183,16 +192,93 @@ def choose_splitters(all_samples: torch.Tensor, world: int) -> torch.Tensor:
     return torch.tensor(bounds, dtype=torch.int64)
 
 
+class PositiveExchange:
+    """``pooled_measures(mode="rank")`` with the exchange of the positives hidden behind the per-image pass.
+
+    Attach one to the ``ood.KeyPool`` of the evaluation (``pool.exchange = PositiveExchange(...)``): every
+    ``eval_segments(..., pool=pool, method="rank")`` batch then exports its positives' score keys into the next
+    fixed-capacity slot and all-gathers that slot right away -- asynchronously, on NCCL's stream, while the head and metric
+    kernels of the following batches run (NVLink is otherwise idle during that phase).  When the pooled stage starts,
+    every rank already holds every rank's positives: no count exchange, no local sort, no bulk all-gather on the critical
+    path; one read of the slot headers sizes the merge.  Slot record (int32 words): [0:2] int64 keys in the slot,
+    [2:10] the pool's running (n_pos, n_nan, n_out_of_window, -) as int64, [10:12] int64 keys pooled so far, then the
+    keys.  Collective: every rank must publish the same number of slots per evaluation (``publish_empty`` pads)."""
+    HDR = 12
+
+    def __init__(self, device, slot_keys: int, max_slots: int, group=None):
+        self.device = torch.device(device)
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.slot_keys = (int(slot_keys) + 1) & ~1
+        self.stride = self.HDR + self.slot_keys
+        self.max_slots = int(max_slots)
+        self.local = torch.zeros(self.max_slots, self.stride, dtype=torch.int32, device=self.device)
+        self.gathered = torch.zeros(self.max_slots, self.world, self.stride, dtype=torch.int32, device=self.device)
+        self.comm = torch.cuda.Stream(self.device) if self.device.type == "cuda" else None
+        self.works = []
+        self.n = 0
+        self._open = False
+
+    def begin(self):
+        """start of an evaluation (all slots of the previous one must have been consumed by ``finish``)"""
+        self.finish()
+        self.n = 0
+
+    def next_slot(self, need: int):
+        """(keys int32 [slot_keys], count int64 [1]) of the next slot, count zeroed; ``need`` = keys the batch may export"""
+        if self.n >= self.max_slots:
+            raise ValueError(f"PositiveExchange: more than max_slots = {self.max_slots} batches in one evaluation")
+        if need > self.slot_keys:
+            raise ValueError(f"PositiveExchange: a batch may export {need} keys, slot capacity is {self.slot_keys}")
+        slot = self.local[self.n]
+        slot[:self.HDR].zero_()
+        self._open = True
+        return slot[self.HDR:], slot[:2].view(torch.int64)
+
+    def publish(self, running_stats: torch.Tensor, keys_so_far: int):
+        """header <- the pool's running counts; launch the all-gather of the slot (returns at once)"""
+        if not self._open:
+            raise ValueError("PositiveExchange.publish without next_slot")
+        slot = self.local[self.n]
+        slot[2:10].view(torch.int64).copy_(running_stats.view(-1)[:4])
+        slot[10:12].view(torch.int64).fill_(int(keys_so_far))
+        out = self.gathered[self.n]
+        if self.comm is not None:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(self.comm):
+                self.comm.wait_event(ev)
+                w = dist.all_gather_into_tensor(out.view(-1), slot, group=self.group, async_op=True)
+        else:
+            w = dist.all_gather(list(out.unbind(0)), slot, group=self.group, async_op=True)
+        self.works.append(w)
+        self.n += 1
+        self._open = False
+
+    def publish_empty(self, running_stats: torch.Tensor, keys_so_far: int):
+        """a slot without keys (a batch that went another way, or padding to the common number of batches)"""
+        self.next_slot(0)
+        self.publish(running_stats, keys_so_far)
+
+    def finish(self) -> torch.Tensor:
+        """the current stream waits for the outstanding all-gathers; [n, world, stride] int32 records"""
+        for w in self.works:
+            w.wait()
+        self.works = []
+        return self.gathered[: self.n]
+
+
 def pooled_measures(conf: torch.Tensor, gt: torch.Tensor, out_labels: Sequence[int] = (13,), *, group=None,
                     recall_level: float = ood.RECALL_LEVEL_DEFAULT, mode: str = "partition", ops=None,
                     workspace: Optional[ood.OodWorkspace] = None, key_base: int = ood.KEY_BASE_NONNEG,
-                    timing: bool = False, keys_and_stats=None):
+                    timing: bool = False, keys_and_stats=None, exchange: Optional["PositiveExchange"] = None):
     """Exact pooled (auroc, aupr, fpr, info) over the (conf, gt) pairs of ALL ranks of ``group``.
     ``conf`` must be non-negative (normalised maps); positives are gt in ``out_labels``; the ranked
     score is -conf like anomaly/eval_ood_traditional.py:139-141.  Collective: every rank must call it.
     ``keys_and_stats`` = (packed keys int32 [n], stats int64 [>=3] = n_pos, n_nan, n_out_of_window), e.g. an
     ``ood.KeyPool``'s ``keys`` / ``stats[0]`` filled by the per-image evaluation: the rank's key generation is skipped
-    (``conf`` / ``gt`` may then be None); the keys may be in any order."""
+    (``conf`` / ``gt`` may then be None); the keys may be in any order.  ``exchange`` (mode="rank"): the
+    ``PositiveExchange`` the per-image batches published their positives to."""
     if mode not in ("partition", "alltoall", "allgather", "rank"):
         raise ValueError("mode must be 'partition', 'alltoall', 'allgather' or 'rank'")
     world = dist.get_world_size(group)
@@ -200,7 +286,9 @@ def pooled_measures(conf: torch.Tensor, gt: torch.Tensor, out_labels: Sequence[i
     dev = conf.device if keys_and_stats is None else keys_and_stats[0].device
     ops = ops or CudaOps(dev, workspace)
     if mode == "rank":
-        return _pooled_measures_rank(conf, gt, out_labels, group, recall_level, ops, key_base, timing, keys_and_stats)
+        return _pooled_measures_rank(conf, gt, out_labels, group, recall_level, ops, key_base, timing, keys_and_stats, exchange)
+    if exchange is not None:
+        raise ValueError("exchange belongs to mode='rank'")
     marks = []
 
     def mark(name):
@@ -309,7 +397,7 @@ def pooled_measures(conf: torch.Tensor, gt: torch.Tensor, out_labels: Sequence[i
     return auroc, aupr, fpr, out
 
 
-def _pooled_measures_rank(conf, gt, out_labels, group, recall_level, ops, key_base, timing, keys_and_stats):
+def _pooled_measures_rank(conf, gt, out_labels, group, recall_level, ops, key_base, timing, keys_and_stats, exchange=None):
     """``pooled_measures(mode="rank")``: the minority-rank form of the pooled metric.  No negative ever leaves its GPU:
 
       1. every rank compacts and radix-sorts the score keys of ITS positives (~1 % of the pairs);
@@ -342,40 +430,66 @@ def _pooled_measures_rank(conf, gt, out_labels, group, recall_level, ops, key_ba
             pos_keys, pos_count = keys_and_stats[2:]
     mark("keygen")
     n_local = keys.numel()
-    # local counts -> every rank (one small all_gather; the host needs them to size the exchange)
-    have = pos_count.view(-1)[:1].to(torch.int64) if pos_count is not None else torch.full((1,), -1, dtype=torch.int64, device=dev)
-    mine = torch.cat([stats[:3].to(torch.int64), torch.tensor([n_local], dtype=torch.int64, device=dev), have])
-    allc = [torch.empty_like(mine) for _ in range(world)]
-    dist.all_gather(allc, mine, group=group)
-    allc = torch.stack(allc).cpu()                                      # [rank, (n_pos, n_nan, n_oow, n, positives on hand)]
-    total_pos, n_nan, n_oow, total_n = [int(v) for v in allc[:, :4].sum(0).tolist()]
-    if n_nan:
-        raise ValueError("Input contains NaN.")
-    if n_oow:
-        raise ValueError("pooled_measures: conf must be non-negative (keys left the packed 31-bit window)")
-    pos_counts = [int(v) for v in allc[:, 0].tolist()]
-    mark("counts_exchange")
     me = dist.get_rank(group)
-    if pos_keys is not None and int(allc[me, 4]) == pos_counts[me] and pos_counts[me] <= pos_keys.numel():
-        srt = ops.sort31(pos_keys[: pos_counts[me]], "rk_local")                # the list the per-image pass left
-    else:
-        srt = ops.sorted_positive_keys(keys, pos_counts[me])                    # int32 [n_pos_local], ascending
-    mark("local_positive_sort")
-    pmax = max(pos_counts) if pos_counts else 0
-    out = {"n_pos": total_pos, "n_neg": total_n - total_pos, "n_groups": -1, "mode": "rank",
-           "exchanged_bytes": 4 * (sum(pos_counts) - pos_counts[dist.get_rank(group)])}
-    if total_pos == 0 or total_pos == total_n:
-        return float("nan"), float("nan"), float("nan"), out
-    pad = ops.empty_keys(pmax, "rk_pad")
-    pad[: srt.numel()].copy_(srt)
-    shards = [ops.empty_keys(pmax, f"rk_shard{r}") for r in range(world)]
-    dist.all_gather(shards, pad, group=group)
-    allpos = ops.empty_keys(total_pos, "rk_all")
-    off = 0
-    for r in range(world):
-        allpos[off: off + pos_counts[r]].copy_(shards[r][: pos_counts[r]])
-        off += pos_counts[r]
-    mark("positive_allgather")
+    allpos = hold = None
+    if exchange is not None and exchange.n > 0:
+        # the batches published their positives while the per-image pass ran: all that is left is to wait for the last
+        # all-gathers and to read the slot headers (identical on every rank, so every rank takes the same branch below)
+        rec = exchange.finish()                                          # [batches, world, stride] int32
+        nb = rec.shape[0]
+        hdr = rec[:, :, :exchange.HDR].contiguous().cpu().view(torch.int64)   # [batches, world, (count, n_pos, n_nan, n_oow, -, n)]
+        last = hdr[-1]
+        total_pos, n_nan, n_oow, total_n = int(last[:, 1].sum()), int(last[:, 2].sum()), int(last[:, 3].sum()), int(last[:, 5].sum())
+        if n_nan:
+            raise ValueError("Input contains NaN.")
+        if n_oow:
+            raise ValueError("pooled_measures: conf must be non-negative (keys left the packed 31-bit window)")
+        mark("positive_exchange_wait")
+        out = {"n_pos": total_pos, "n_neg": total_n - total_pos, "n_groups": -1, "mode": "rank",
+               "exchanged_bytes": 4 * exchange.stride * (world - 1) * nb, "positives_from": "slots"}
+        if total_pos == 0 or total_pos == total_n:
+            return float("nan"), float("nan"), float("nan"), out
+        complete = bool((hdr[:, :, 0].sum(0) == last[:, 1]).all()) and bool((hdr[:, :, 0] <= exchange.slot_keys).all()) \
+            and bool((hdr[:, :, 0] >= 0).all())
+        if not complete:  # some batch kept its positives to itself (e.g. an overflowed segment): compact + all-gather below
+            hold = out
+        else:
+            allpos = ops.slots_gather(rec.reshape(nb * world, exchange.stride), exchange.HDR, exchange.slot_keys, total_pos)
+            mark("slots_gather")
+    if allpos is None:
+        # local counts -> every rank (one small all_gather; the host needs them to size the exchange)
+        have = pos_count.view(-1)[:1].to(torch.int64) if pos_count is not None else torch.full((1,), -1, dtype=torch.int64, device=dev)
+        mine = torch.cat([stats[:3].to(torch.int64), torch.tensor([n_local], dtype=torch.int64, device=dev), have])
+        allc = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allc, mine, group=group)
+        allc = torch.stack(allc).cpu()                                      # [rank, (n_pos, n_nan, n_oow, n, positives on hand)]
+        total_pos, n_nan, n_oow, total_n = [int(v) for v in allc[:, :4].sum(0).tolist()]
+        if n_nan:
+            raise ValueError("Input contains NaN.")
+        if n_oow:
+            raise ValueError("pooled_measures: conf must be non-negative (keys left the packed 31-bit window)")
+        pos_counts = [int(v) for v in allc[:, 0].tolist()]
+        mark("counts_exchange")
+        if pos_keys is not None and int(allc[me, 4]) == pos_counts[me] and pos_counts[me] <= pos_keys.numel():
+            srt = ops.sort31(pos_keys[: pos_counts[me]], "rk_local")                # the list the per-image pass left
+        else:
+            srt = ops.sorted_positive_keys(keys, pos_counts[me])                    # int32 [n_pos_local], ascending
+        mark("local_positive_sort")
+        pmax = max(pos_counts) if pos_counts else 0
+        out = {"n_pos": total_pos, "n_neg": total_n - total_pos, "n_groups": -1, "mode": "rank", "positives_from": "allgather",
+               "exchanged_bytes": 4 * (sum(pos_counts) - pos_counts[me]) + (hold["exchanged_bytes"] if hold else 0)}
+        if total_pos == 0 or total_pos == total_n:
+            return float("nan"), float("nan"), float("nan"), out
+        pad = ops.empty_keys(pmax, "rk_pad")
+        pad[: srt.numel()].copy_(srt)
+        shards = [ops.empty_keys(pmax, f"rk_shard{r}") for r in range(world)]
+        dist.all_gather(shards, pad, group=group)
+        allpos = ops.empty_keys(total_pos, "rk_all")
+        off = 0
+        for r in range(world):
+            allpos[off: off + pos_counts[r]].copy_(shards[r][: pos_counts[r]])
+            off += pos_counts[r]
+        mark("positive_allgather")
     merged = ops.sort31(allpos, "rk_merge")
     S, pc, G = ops.unique_groups(merged)
     mark("merge_positives")

@@ -79,6 +79,9 @@ class KeyPool:
         # evaluation then skips its compaction pass over all keys.  Allocated by the first such batch.
         self.pos = None
         self.pos_count = torch.zeros(1, dtype=torch.int64, device=self.device)
+        # multi-GPU, method="rank": a distributed.PositiveExchange that ships every batch's positives to all ranks at once
+        # (set by the caller; every eval_segments call on this pool then publishes exactly one slot)
+        self.exchange = None
         self.reset()
 
     def reset(self):
@@ -87,6 +90,8 @@ class KeyPool:
         self.hist_ok = True      # every contribution so far also left its digit histograms (method="sort" batches)
         self.stats.zero_()
         self.pos_count.zero_()
+        if getattr(self, "exchange", None) is not None:
+            self.exchange.begin()
 
     def _take(self, n: int, signature) -> torch.Tensor:
         if self.n + n > self.capacity:
@@ -219,6 +224,8 @@ def eval_segments(values: torch.Tensor, n_seg: int, seg_len: int, *, gt: Optiona
             check(lib().dml_ood_pool_histograms(ptr(scratch), scratch.numel(), ptr(stats), n_seg, seg_len, ptr(pool.scratch),
                                                 pool.scratch.numel() if pool.scratch is not None else 0, pool.capacity,
                                                 ptr(pool.stats), 1 if pool.n == n else 0, s), "dml_ood_pool_histograms")
+            if pool.exchange is not None:        # a sort-path batch keeps its positives: an empty slot keeps the ranks in step
+                pool.exchange.publish_empty(pool.stats, pool.n)
         check(lib().dml_ood_eval_segments(ptr(keys), ptr(stats), n_seg, seg_len, recall_level, ptr(scratch),
                                           scratch.numel(), 1 if fused_hist else 0, ptr(results), s), "dml_ood_eval_segments")
     return results, stats
@@ -278,10 +285,18 @@ def _eval_segments_rank(values, n_seg, seg_len, gt, out_labels, positive, score_
             pool.hist_ok = False       # this batch left keys and counts, no digit histograms
             check(lib().dml_ood_pool_histograms(None, 0, ptr(stats), n_seg, seg_len, None, 0, pool.capacity, ptr(pool.stats),
                                                 1 if pool.n == n else 0, s), "dml_ood_pool_histograms")
-            if pool.pos is None:
-                pool.pos = torch.empty(max(1 << 20, pool.capacity // 16), dtype=torch.int32, device=dev)
-            check(lib().dml_ood_rank_export_positives(ptr(rws), rws.numel(), n_seg, pos_capacity, ptr(pool.pos), pool.pos.numel(),
-                                                      ptr(pool.pos_count), s), "dml_ood_rank_export_positives")
+            if pool.exchange is not None:
+                # multi-GPU: the batch's positives go into the exchange's next slot and travel to the other ranks while
+                # the following batches are evaluated (distributed.PositiveExchange)
+                slot_keys, slot_count = pool.exchange.next_slot(n_seg * pos_capacity)
+                check(lib().dml_ood_rank_export_positives(ptr(rws), rws.numel(), n_seg, pos_capacity, ptr(slot_keys),
+                                                          slot_keys.numel(), ptr(slot_count), s), "dml_ood_rank_export_positives")
+                pool.exchange.publish(pool.stats, pool.n)
+            else:
+                if pool.pos is None:
+                    pool.pos = torch.empty(max(1 << 20, pool.capacity // 16), dtype=torch.int32, device=dev)
+                check(lib().dml_ood_rank_export_positives(ptr(rws), rws.numel(), n_seg, pos_capacity, ptr(pool.pos), pool.pos.numel(),
+                                                          ptr(pool.pos_count), s), "dml_ood_rank_export_positives")
     return results, stats
 
 

@@ -97,6 +97,15 @@ class NumpyOps:
     def empty_keys(self, n, tag):
         return torch.empty(n, dtype=torch.int32)
 
+    def slots_gather(self, records, hdr_words, slot_keys, total):
+        out = []
+        for r in records.numpy():
+            c = int(r[:2].view(np.int64)[0])
+            out.append(r[hdr_words: hdr_words + min(max(c, 0), slot_keys)])
+        k = np.concatenate(out) if out else np.zeros(0, np.int32)
+        assert k.size == total
+        return torch.from_numpy(k.copy())
+
     # ---- minority-rank mode (distributed.pooled_measures(mode="rank")): NumPy restatement of csrc/ood_pool_rank.cu ----
     def sorted_positive_keys(self, keys, n_pos):
         k = _u(keys)

@@ -46,7 +46,7 @@ def _worker(rank, world, port, case, mode, q):
         from dml_b200 import distributed as D
         from tests.np_ops import NumpyOps
         conf, gt = _make_shard(rank, case)
-        if case.endswith("+keys"):
+        if "+keys" in case:
             # keys handed over by the per-image evaluation (an ood.KeyPool on the GPU): already generated, and left
             # sorted inside every 1000-pair "image" by the per-image sorts
             ops = NumpyOps()
@@ -54,8 +54,29 @@ def _worker(rank, world, port, case, mode, q):
             k = keys.numpy().view(np.uint32).copy()
             for s0 in range(0, k.size, 1000):
                 k[s0:s0 + 1000].sort()
+            ex = None
+            if "+exchange" in case:
+                # what ood.eval_segments(pool=...) does per batch on the GPU: export the batch's positives into the next
+                # slot, publish it with the pool's running counts; 8 slots on every rank (short shards pad with empty ones)
+                ex = D.PositiveExchange("cpu", slot_keys=1000, max_slots=8)
+                ex.begin()
+                run = np.zeros(4, np.int64)
+                for b in range(8):
+                    kb = k[b * 1000:(b + 1) * 1000]
+                    pos = (kb[(kb & 1) == 1] >> 1).astype(np.uint32)
+                    run[0] += pos.size
+                    done = min((b + 1) * 1000, k.size)
+                    if kb.size == 0 or ("+hold" in case and rank == 0 and b == 1):
+                        ex.publish_empty(torch.from_numpy(run.copy()), done)       # (+hold: a batch that kept its positives)
+                        continue
+                    slot, cnt = ex.next_slot(1000)
+                    slot[:pos.size] = torch.from_numpy(pos.view(np.int32).copy())
+                    cnt[0] = pos.size
+                    ex.publish(torch.from_numpy(run.copy()), done)
             a, p, f, info = D.pooled_measures(None, None, (13,), mode=mode, ops=ops,
-                                              keys_and_stats=(torch.from_numpy(k.view(np.int32)), stats))
+                                              keys_and_stats=(torch.from_numpy(k.view(np.int32)), stats), exchange=ex)
+            if ex is not None:
+                assert info["positives_from"] == ("allgather" if "+hold" in case else "slots")
         else:
             a, p, f, info = D.pooled_measures(torch.from_numpy(conf), torch.from_numpy(gt), (13,), mode=mode, ops=NumpyOps())
         vals = torch.tensor([[0.5 + 0.1 * rank, 0.2, 0.3], [float("nan")] * 3, [0.7, 0.4, 0.1]], dtype=torch.float64)
@@ -73,7 +94,9 @@ def _worker(rank, world, port, case, mode, q):
                                              (3, "empty_rank", "partition"), (2, "ties+keys", "partition"),
                                              (3, "empty_rank+keys", "partition"), (2, "plain+keys", "allgather"),
                                              (2, "plain", "rank"), (2, "ties", "rank"), (3, "skewed", "rank"),
-                                             (3, "empty_rank", "rank"), (2, "ties+keys", "rank")])
+                                             (3, "empty_rank", "rank"), (2, "ties+keys", "rank"),
+                                             (2, "plain+keys+exchange", "rank"), (3, "empty_rank+keys+exchange", "rank"),
+                                             (3, "skewed+keys+exchange+hold", "rank")])
 def test_pooled_measures_gloo(world, case, mode):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()

@@ -40,7 +40,24 @@ def _worker(rank, world, port, mode, q):
     try:
         from dml_b200 import distributed as D
         conf, gt = _shard(rank)
-        if mode.endswith("+pool"):
+        if "+exchange" in mode:
+            # the bench's multi-GPU flow: rank-path batches publish their positives to all ranks as they go
+            # (PositiveExchange); "+sortbatch": one batch takes the sort path and keeps its positives -> the pooled stage
+            # notices the shortfall in the slot headers and falls back to compaction + all-gather
+            from dml_b200 import ood
+            pool = ood.KeyPool(conf.size, "cuda", histograms=False)
+            pool.exchange = D.PositiveExchange("cuda", slot_keys=6 * 4096, max_slots=4)
+            c, g = torch.from_numpy(conf).cuda().view(10, -1), torch.from_numpy(gt).cuda().view(10, -1)
+            for rep in range(2):                       # twice: reset() must recycle the slots
+                pool.reset()
+                for bi, (s0, s1) in enumerate(((0, 6), (6, 10))):
+                    m = "sort" if ("+sortbatch" in mode and bi == 1) else "rank"
+                    ood.eval_segments(c[s0:s1], s1 - s0, c.shape[1], gt=g[s0:s1], out_labels=(13,), pool=pool, method=m,
+                                      pos_capacity=4096)
+                a, p, f, info = D.pooled_measures(None, None, (13,), mode="rank", keys_and_stats=(pool.keys, pool.stats[0]),
+                                                  exchange=pool.exchange)
+            assert info["positives_from"] == ("allgather" if "+sortbatch" in mode else "slots")
+        elif mode.endswith("+pool"):
             # the bench's flow: the per-image evaluation (10 "images" of 30 000 pairs, two batches) leaves its keys and
             # counts in an ood.KeyPool; the pooled exchange starts from those keys instead of generating them again
             from dml_b200 import ood
@@ -58,7 +75,8 @@ def _worker(rank, world, port, mode, q):
 
 
 @pytest.mark.parametrize("world", [1, 2])
-@pytest.mark.parametrize("mode", ["partition", "alltoall", "allgather", "partition+pool", "allgather+pool", "rank", "rank+pool"])
+@pytest.mark.parametrize("mode", ["partition", "alltoall", "allgather", "partition+pool", "allgather+pool", "rank", "rank+pool",
+                                  "rank+pool+exchange", "rank+pool+exchange+sortbatch"])
 def test_pooled_measures_nccl(world, mode):
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
