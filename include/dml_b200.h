@@ -409,6 +409,26 @@ DML_API size_t dml_ood_partition_workspace_bytes(int32_t n_buckets);
 DML_API int dml_ood_partition(const uint32_t* keys, int64_t n, const uint32_t* bounds, int32_t n_buckets, uint32_t* out,
                       long long* counts, void* workspace, size_t workspace_bytes, dml_stream_t stream);
 
+/* ------------------------------------------------------------------------------------ *
+ * (f-4) Input side of the multi-scale evaluation: ValDataset's resize + normalisation loop
+ *   anomaly/dataset.py:11-21,281-297  imresize(img, (w, h), 'bilinear') = PIL.Image.resize(.., BILINEAR) per scale
+ *   anomaly/dataset.py:65-70          img_transform: float32 / 255, HWC -> CHW, Normalize(mean, std)
+ * Bit-exact with Pillow's 8-bit two-pass resampling (integer coefficients, uint8 intermediate) followed by the
+ * reference's float32 arithmetic ((v / 255) - mean) / std.
+ *   dml_resize_ksize      taps per output index of one axis (host)
+ *   dml_resize_coeffs     host: bounds[2 i] = first tap, bounds[2 i + 1] = tap count, coeffs[i * ksize + t] = weight 2^22
+ *   dml_resize_bilinear_normalize   device: image uint8 [B, H, W, 3] -> out float32 [B, 3, out_h, out_w]; the four
+ *                         tables are DEVICE copies of dml_resize_coeffs' output; mean / stdv are HOST float[3];
+ *                         max_rows_per_tile >= the input rows any 8 consecutive output rows touch
+ *                         (max over i of bounds_y[2 min(i + 7, out_h - 1)] + count - bounds_y[2 i]).
+ * ------------------------------------------------------------------------------------ */
+DML_API int32_t dml_resize_ksize(int32_t in_size, int32_t out_size);
+DML_API int dml_resize_coeffs(int32_t in_size, int32_t out_size, int32_t* bounds, int32_t* coeffs, int32_t ksize);
+DML_API int dml_resize_bilinear_normalize(const uint8_t* image, int32_t B, int32_t H, int32_t W, const int32_t* bounds_x,
+                                  const int32_t* coeffs_x, int32_t ksize_x, const int32_t* bounds_y, const int32_t* coeffs_y,
+                                  int32_t ksize_y, int32_t out_h, int32_t out_w, int32_t max_rows_per_tile, const float* mean,
+                                  const float* stdv, float* out, dml_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -119,6 +119,11 @@ SIGNATURES = {
     "dml_ood_rank_export_positives": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p,
                                                 C.c_void_p]),
     "dml_ood_pos_compact": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "dml_resize_ksize": (C.c_int32, [C.c_int32, C.c_int32]),
+    "dml_resize_coeffs": (C.c_int, [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32]),
+    "dml_resize_bilinear_normalize": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
+                                                C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
+                                                C.c_void_p, C.c_void_p, C.c_void_p]),
     "dml_ood_slots_gather": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]),
     "dml_ood_unique_workspace_bytes": (C.c_size_t, [C.c_int64]),
     "dml_ood_unique_counts": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
