@@ -429,6 +429,31 @@ DML_API int dml_resize_bilinear_normalize(const uint8_t* image, int32_t B, int32
                                   int32_t ksize_y, int32_t out_h, int32_t out_w, int32_t max_rows_per_tile, const float* mean,
                                   const float* stdv, float* out, dml_stream_t stream);
 
+/* ------------------------------------------------------------------------------------ *
+ * (f-4) Synchronised batch normalisation, one process per GPU (NCHW fp32):
+ *   anomaly/lib/nn/modules/batchnorm.py:57-88,121-139 (_SynchronizedBatchNorm.forward / _compute_mean_std)
+ *   dml_bn_stats           forward (dy = mean = NULL): sums[c] = sum x, sums[C + c] = sum x^2 over (B, HW);
+ *                          backward: sums[c] = sum dy, sums[C + c] = sum dy (x - mean[c]).  Device doubles [2C]; the caller
+ *                          all-reduces them across ranks (NCCL) before the next call.
+ *   dml_bn_finalize        all-reduced forward sums + global element count (*count: DEVICE double, all-reduced with the
+ *                          sums, so no host synchronisation sits between the kernels; must exceed 1) -> mean, inv_std = clamp(var, eps)^-1/2,
+ *                          clamped[c] = 1 where the clamp is active; with tmp_running_mean != NULL also the reference's
+ *                          moving averages (_tmp_running_mean / _tmp_running_var / _running_iter -> running_mean / running_var)
+ *   dml_bn_apply           y = (x - mean) (inv_std weight) + bias       (weight / bias may be NULL)
+ *   dml_bn_backward_apply  dx from the all-reduced backward sums and the global count
+ * ------------------------------------------------------------------------------------ */
+DML_API size_t dml_bn_workspace_bytes(int32_t B, int32_t C, int64_t HW);
+DML_API int dml_bn_stats(const float* x, const float* dy, const float* mean, int32_t B, int32_t C, int64_t HW, double* sums,
+                 void* workspace, size_t workspace_bytes, dml_stream_t stream);
+DML_API int dml_bn_finalize(const double* sums, const double* count, float eps, float momentum, int32_t C, float* tmp_running_mean,
+                    float* tmp_running_var, float* running_iter, float* running_mean, float* running_var, float* mean,
+                    float* inv_std, uint8_t* clamped, dml_stream_t stream);
+DML_API int dml_bn_apply(const float* x, const float* mean, const float* inv_std, const float* weight, const float* bias, int32_t B,
+                 int32_t C, int64_t HW, float* y, dml_stream_t stream);
+DML_API int dml_bn_backward_apply(const float* x, const float* dy, const float* mean, const float* inv_std, const float* weight,
+                          const uint8_t* clamped, const double* sums, const double* count, int32_t B, int32_t C, int64_t HW, float* dx,
+                          dml_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

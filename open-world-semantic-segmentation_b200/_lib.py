@@ -119,6 +119,15 @@ SIGNATURES = {
     "dml_ood_rank_export_positives": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p,
                                                 C.c_void_p]),
     "dml_ood_pos_compact": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "dml_bn_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int64]),
+    "dml_bn_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_size_t,
+                               C.c_void_p]),
+    "dml_bn_finalize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "dml_bn_apply": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_void_p,
+                               C.c_void_p]),
+    "dml_bn_backward_apply": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p]),
     "dml_resize_ksize": (C.c_int32, [C.c_int32, C.c_int32]),
     "dml_resize_coeffs": (C.c_int, [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32]),
     "dml_resize_bilinear_normalize": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
