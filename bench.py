@@ -54,8 +54,6 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-pooled", action="store_true")
-    ap.add_argument("--no-fused-gather", action="store_true",
-                    help="minority-rank path: gather the positives in a separate pass over the label map instead of inside the head (A/B)")
     ap.add_argument("--no-overlap-exchange", action="store_true",
                     help="N > 1: exchange the positives after the per-image pass (count exchange + local sort + one bulk all-gather) "
                          "instead of batch by batch behind it (A/B)")
@@ -383,24 +381,19 @@ class Pipeline:
         if time_head:
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             ev0.record()
-        nb = e - s
-        # minority-rank path: the head appends the positives' raw EDS values to the metric pass's list while they are in
-        # registers (no separate gather over the label map)
-        pl = None
-        if self.args.metric_method == "rank" and not self.args.no_fused_gather:
-            pl = ood.PositiveList(self.ws_img, nb, out_labels=(self.k,))
         H.dml_head(x, magnitude=3.0, want_logits=False, label_dtype=torch.uint8, want_eds=True, eds_clamp=400.0,
-                   want_msp=True, want_minmax=True, gt=gt, out=self.outs[ci], positives=pl)
+                   want_msp=True, want_minmax=True, gt=gt, out=self.outs[ci])
         if time_head:
             ev1.record()
             self.head_events.append((ev0, ev1))
+        nb = e - s
         if time_head:
             ev2 = torch.cuda.Event(enable_timing=True)
         # key-gen reads the raw EDS once: normalised conf map, MMSP map, mix map and ranking keys
         res, stats = ood.eval_segments(self.eds[s:e], nb, self.hw, gt=gt, out_labels=(self.k,), score_kind=0,
                                        minmax=self.minmax[s:e], minmax_slot=0, conf_out=self.conf[s:e],
                                        workspace=self.ws_img, msp=self.msp[s:e], msp_norm_out=self.mmsp_c[:nb],
-                                       mix_out=self.mix_c[:nb], pool=self.pool, method=self.args.metric_method, positives=pl)
+                                       mix_out=self.mix_c[:nb], pool=self.pool, method=self.args.metric_method)
         if time_head:
             ev2.record()
             self.metric_events.append((ev1, ev2))

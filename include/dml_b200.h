@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define DML_B200_ABI_VERSION 5
+#define DML_B200_ABI_VERSION 4
 
 #if defined(__GNUC__)
 #define DML_API __attribute__((visibility("default")))
@@ -119,16 +119,6 @@ typedef struct dml_head_params {
                                  square, sum over the embedding dim in torch's CPU order), so that the distance logits are
                                  bit-identical to the reference's on identical embeddings.  Slower; for verification and for
                                  the tiny stride-8 maps of the anomaly path. */
-  /* positives of the OOD metric, gathered while the scores are in registers (optional; needs gt_u8 or gt_i64):
-     pixels whose ground-truth label is in pos_label_mask (bit l = label l, l < 64) append the float bits of their
-     (clamped) EDS value to pos_values[b * pos_capacity + i], i = pos_cursor[b]++ (device, [B], zeroed by the caller;
-     counts past pos_capacity are kept so that the consumer sees the overflow).  Point both into the workspace of
-     dml_ood_rank_segments_pregathered (dml_ood_rank_workspace_layout) and the metric pass skips its own gather over
-     the label map (anomaly/eval_ood_traditional.py:134-141: out_label = seg_label == 13). */
-  uint32_t* pos_values;
-  uint32_t* pos_cursor;
-  int32_t pos_capacity;
-  uint64_t pos_label_mask;
 } dml_head_params;
 
 DML_API int dml_head_forward(const dml_head_params* p, dml_stream_t stream);
@@ -359,19 +349,6 @@ DML_API int dml_ood_scan_range(const uint32_t* sorted_keys, int64_t n, const lon
  * workspace: dml_ood_rank_workspace_bytes(n_seg, pos_capacity).  All pointers device. */
 DML_API size_t dml_ood_rank_workspace_bytes(int32_t n_seg, int32_t pos_capacity);
 DML_API int dml_ood_rank_segments(const float* values, const float* minmax, int32_t minmax_slot, float* conf_out,
-                          const uint8_t* gt_u8, const int64_t* gt_i64, uint64_t out_label_mask, const uint8_t* pos_u8,
-                          int32_t score_kind, uint32_t key_base, int32_t n_seg, int64_t seg_len, uint32_t* keys_out,
-                          long long* seg_stats, const float* msp, float* msp_norm_out, float* mix_out, float lambda,
-                          float thr, int32_t pos_capacity, double recall_level, void* workspace, size_t workspace_bytes,
-                          dml_ood_result* results, dml_stream_t stream);
-
-/* dml_ood_rank_segments whose positives were already appended, RAW (float bits of `values`), to the workspace's list by
- * the kernel that produced `values` (dml_head_params.pos_values / pos_cursor): the gather pass over the label map is
- * skipped, the list is normalised and packed in place before the sort.  dml_ood_rank_workspace_layout returns the byte
- * offsets of that list ([n_seg, pos_capacity] u32) and of its cursors ([n_seg] u32, zeroed by the caller before the
- * producer runs) inside a workspace of dml_ood_rank_workspace_bytes(n_seg, pos_capacity). */
-DML_API int dml_ood_rank_workspace_layout(int32_t n_seg, int32_t pos_capacity, size_t* list_offset, size_t* cursor_offset);
-DML_API int dml_ood_rank_segments_pregathered(const float* values, const float* minmax, int32_t minmax_slot, float* conf_out,
                           const uint8_t* gt_u8, const int64_t* gt_i64, uint64_t out_label_mask, const uint8_t* pos_u8,
                           int32_t score_kind, uint32_t key_base, int32_t n_seg, int64_t seg_len, uint32_t* keys_out,
                           long long* seg_stats, const float* msp, float* msp_norm_out, float* mix_out, float lambda,

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libdml_b200.so")
 
 DML_OK = 0
-ABI_VERSION = 5
+ABI_VERSION = 4
 
 c_f32p = C.c_void_p
 c_void_p = C.c_void_p
@@ -35,7 +35,6 @@ class HeadParams(C.Structure):
         ("want_eds_minmax", C.c_int32), ("want_msp_minmax", C.c_int32),
         ("gt_u8", C.c_void_p), ("gt_i64", C.c_void_p), ("confusion", C.c_void_p),
         ("conf_rows", C.c_int32), ("conf_cols", C.c_int32), ("reference_order", C.c_int32),
-        ("pos_values", C.c_void_p), ("pos_cursor", C.c_void_p), ("pos_capacity", C.c_int32), ("pos_label_mask", C.c_uint64),
     ]
 
 
@@ -117,11 +116,6 @@ SIGNATURES = {
                                         C.c_void_p, C.c_int32, C.c_uint32, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_int32, C.c_double,
                                         C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
-    "dml_ood_rank_segments_pregathered": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64,
-                                                    C.c_void_p, C.c_int32, C.c_uint32, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p,
-                                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_int32, C.c_double,
-                                                    C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
-    "dml_ood_rank_workspace_layout": (C.c_int, [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "dml_ood_rank_export_positives": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p,
                                                 C.c_void_p]),
     "dml_ood_pos_compact": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),

@@ -138,7 +138,6 @@ int dml_head_forward(const dml_head_params* p, dml_stream_t stream_) {
   }
   if (p->B > 65535) return DML_ERR_INVALID_ARG;
   if (p->reference_order && (mode != HEAD_IDENT || p->D >= 16 || !p->logits)) return DML_ERR_INVALID_ARG;
-  if (p->pos_values && (!p->pos_cursor || p->pos_capacity < 1 || (!p->gt_u8 == !p->gt_i64))) return DML_ERR_INVALID_ARG;
   const long long hw = (long long)p->H * p->W;
   if (p->B == 0 || hw == 0) return DML_OK;
 
@@ -153,13 +152,12 @@ int dml_head_forward(const dml_head_params* p, dml_stream_t stream_) {
   a.want_eds_mm = p->want_eds_minmax; a.want_msp_mm = p->want_msp_minmax;
   a.gt_u8 = p->gt_u8; a.gt_i64 = (const long long*)p->gt_i64; a.conf = p->confusion;
   a.crow = p->conf_rows; a.ccol = p->conf_cols;
-  a.pos_values = p->pos_values; a.pos_cursor = p->pos_cursor; a.pos_cap = p->pos_capacity; a.pos_mask = p->pos_label_mask;
   a.B = p->B; a.K = p->K; a.HW = hw;
   a.out_mask = (a.label_u8 ? OUT_LABEL_U8 : 0u) | (a.label_i64 ? OUT_LABEL_I64 : 0u) | (a.maxlogit ? OUT_MAXLOGIT : 0u) |
                (a.eds ? OUT_EDS : 0u) | (a.msp ? OUT_MSP : 0u) |
                ((a.minmax && (a.want_eds_mm || a.want_msp_mm)) ? OUT_MINMAX : 0u) | (a.conf ? OUT_CONF : 0u) |
                (a.gt_u8 ? OUT_GT_U8 : 0u) | (a.logits ? OUT_LOGITS : 0u) | (a.feat ? OUT_FEAT : 0u) |
-               (a.novel_dist ? OUT_NOVEL_DIST : 0u) | (a.pos_values ? OUT_POS : 0u);
+               (a.novel_dist ? OUT_NOVEL_DIST : 0u);
 
   if (a.minmax && (a.want_eds_mm || a.want_msp_mm)) {
     const int n4 = p->B * 4;

@@ -55,12 +55,6 @@ struct HeadArgs {
   const long long* gt_i64;
   unsigned long long* conf;
   int crow, ccol;
-  // positives of the OOD metric (gt label in pos_mask) appended per image while the scores are in registers:
-  // pos_values[b * pos_cap + i] = float bits of the (clamped) EDS value, i = running count pos_cursor[b]
-  unsigned int* pos_values;
-  unsigned int* pos_cursor;
-  int pos_cap;
-  unsigned long long pos_mask;
   int B, K;
   long long HW;
   unsigned out_mask;  // OUT_* bits: which outputs are wanted (hoists the pointer tests out of the kernel)
@@ -77,7 +71,7 @@ struct HeadArgs {
 };
 
 enum : unsigned { OUT_LABEL_U8 = 1u, OUT_LABEL_I64 = 2u, OUT_MAXLOGIT = 4u, OUT_EDS = 8u, OUT_MSP = 16u, OUT_MINMAX = 32u,
-                  OUT_CONF = 64u, OUT_GT_U8 = 128u, OUT_LOGITS = 256u, OUT_FEAT = 512u, OUT_NOVEL_DIST = 1024u, OUT_POS = 2048u };
+                  OUT_CONF = 64u, OUT_GT_U8 = 128u, OUT_LOGITS = 256u, OUT_FEAT = 512u, OUT_NOVEL_DIST = 1024u };
 constexpr int HEAD_TILES_PER_BLOCK = 4;  // consecutive tiles of one image per CTA: block-level work is amortised
 
 // -(sum_d (x_d - mu_d)^2) in float64, in NumPy's pairwise-summation order for a contiguous
@@ -770,68 +764,36 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_kernel(const HeadArgs a) {
     }
   }
 
-  // ---- ground truth: fused confusion counts (block-shared histogram, flushed once after the tile loop) and the
-  //      positives' list of the OOD metric ------------------------------------------------------------------------
-  if (om & (OUT_CONF | OUT_POS)) {
-    int gl[VEC];
+  // ---- fused confusion counts (block-shared histogram, flushed once after the tile loop) -----------
+  if (om & OUT_CONF) {
+    int bin[VEC];
 #pragma unroll
-    for (int v = 0; v < VEC; ++v) gl[v] = -1;
+    for (int v = 0; v < VEC; ++v) bin[v] = -1;
     if (active) {
       if (om & OUT_GT_U8) {
+        unsigned char g[VEC];
         if constexpr (VEC == 4) {
           const uchar4 t = *reinterpret_cast<const uchar4*>(a.gt_u8 + pix);
-          gl[0] = t.x; gl[1] = t.y; gl[2] = t.z; gl[3] = t.w;
+          g[0] = t.x; g[1] = t.y; g[2] = t.z; g[3] = t.w;
         } else if constexpr (VEC == 2) {
           const uchar2 t = *reinterpret_cast<const uchar2*>(a.gt_u8 + pix);
-          gl[0] = t.x; gl[1] = t.y;
+          g[0] = t.x; g[1] = t.y;
         } else {
-          gl[0] = a.gt_u8[pix];
+          g[0] = a.gt_u8[pix];
         }
+#pragma unroll
+        for (int v = 0; v < VEC; ++v)
+          if ((int)g[v] < a.crow && label[v] < a.ccol) bin[v] = (int)g[v] * a.ccol + label[v];
       } else {
 #pragma unroll
         for (int v = 0; v < VEC; ++v) {
           const long long g = a.gt_i64[pix + v];
-          gl[v] = (g >= 0 && g < 0x7fffffff) ? (int)g : -1;
+          if (g >= 0 && g < a.crow && label[v] < a.ccol) bin[v] = (int)g * a.ccol + label[v];
         }
       }
     }
-    if (om & OUT_CONF) {
-      int bin[VEC];
 #pragma unroll
-      for (int v = 0; v < VEC; ++v) bin[v] = (gl[v] >= 0 && gl[v] < a.crow && label[v] < a.ccol) ? gl[v] * a.ccol + label[v] : -1;
-#pragma unroll
-      for (int v = 0; v < VEC; ++v) warp_histogram_add(s_conf, bin[v]);
-    }
-    if (om & OUT_POS) {
-      // one list reservation per warp and step (most warps see no positive at all); order inside the list is irrelevant
-      unsigned flags = 0u;
-#pragma unroll
-      for (int v = 0; v < VEC; ++v)
-        if (gl[v] >= 0 && gl[v] < 64 && ((a.pos_mask >> gl[v]) & 1ull)) flags |= 1u << v;
-      const int c = __popc(flags);
-      if (__ballot_sync(0xffffffffu, c > 0) != 0u) {
-        const int lane = threadIdx.x & 31;
-        int incl = c;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const int n = __shfl_up_sync(0xffffffffu, incl, o);
-          if (lane >= o) incl += n;
-        }
-        const int total = __shfl_sync(0xffffffffu, incl, 31);
-        unsigned wbase = 0u;
-        if (lane == 31) wbase = atomicAdd(a.pos_cursor + b, (unsigned)total);
-        wbase = __shfl_sync(0xffffffffu, wbase, 31);
-        unsigned dst = wbase + (unsigned)(incl - c);
-        unsigned int* out = a.pos_values + (size_t)b * a.pos_cap;
-#pragma unroll
-        for (int v = 0; v < VEC; ++v) {
-          if ((flags >> v) & 1u) {
-            if (dst < (unsigned)a.pos_cap) out[dst] = __float_as_uint(eds[v]);
-            ++dst;
-          }
-        }
-      }
-    }
+    for (int v = 0; v < VEC; ++v) warp_histogram_add(s_conf, bin[v]);
   }
   }  // tile loop
 

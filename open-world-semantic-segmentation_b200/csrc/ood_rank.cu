@@ -130,13 +130,10 @@ __global__ void __launch_bounds__(256) pos_gather_kernel(const float* __restrict
 //    one shared atomic per key, then every bucket (a handful of keys) is insertion-sorted by one thread.
 //    Otherwise: bitonic network over the padded list.
 // ---------------------------------------------------------------------------------------------
-// raw_values != 0: the list holds the RAW values (float bit patterns) a producer kernel appended while it computed them
-// (the distance head: dml_head_params.pos_values); they are normalised and packed here, in place, before the sort.
-__global__ void __launch_bounds__(RANK_THREADS) pos_sort_kernel(uint32_t* __restrict__ plist, const uint32_t* __restrict__ cursor,
+__global__ void __launch_bounds__(RANK_THREADS) pos_sort_kernel(const uint32_t* __restrict__ plist, const uint32_t* __restrict__ cursor,
                                                                 int cap, uint32_t key_base, uint32_t* __restrict__ S,
                                                                 uint32_t* __restrict__ pc, uint32_t* __restrict__ cnt,
-                                                                uint32_t* __restrict__ Gout, unsigned long long* __restrict__ seg_stats,
-                                                                const float* __restrict__ minmax, int slot, int kind, int raw_values) {
+                                                                uint32_t* __restrict__ Gout, unsigned long long* __restrict__ seg_stats) {
   extern __shared__ uint32_t s_k[];                        // [n2(cap)] sorted keys | [NB + 1] bucket offsets | u16 [BUCKET_SORT_MAX] ranks
   __shared__ uint32_t s_w[RANK_THREADS / 32];
   __shared__ uint32_t s_mn, s_mx, s_big;
@@ -153,15 +150,7 @@ __global__ void __launch_bounds__(RANK_THREADS) pos_sort_kernel(uint32_t* __rest
   while (n2 < P) n2 <<= 1;
   int n2cap = 2;
   while (n2cap < cap) n2cap <<= 1;
-  uint32_t* src = plist + (size_t)seg * cap;
-  if (raw_values) {
-    const Norm nm = load_norm(minmax, seg, slot);
-    for (int i = tid; i < P; i += RANK_THREADS) {
-      unsigned d0 = 0, d1 = 0;
-      src[i] = pack_key(apply_norm(nm, __uint_as_float(src[i])), kind, true, key_base, d0, d1) >> 1;
-    }
-    __syncthreads();
-  }
+  const uint32_t* src = plist + (size_t)seg * cap;
   bool sorted = false;
   if (P > 64 && P <= BUCKET_SORT_MAX) {
     uint32_t* s_off = s_k + n2cap;                                              // [NB + 1]
@@ -577,20 +566,12 @@ size_t dml_ood_rank_workspace_bytes(int32_t n_seg, int32_t pos_capacity) {
   return make_rank_ws(n_seg, pos_capacity).off_end;
 }
 
-int dml_ood_rank_workspace_layout(int32_t n_seg, int32_t pos_capacity, size_t* list_offset, size_t* cursor_offset) {
-  if (n_seg <= 0 || pos_capacity <= 0 || !list_offset || !cursor_offset) return DML_ERR_INVALID_ARG;
-  const RankWs w = make_rank_ws(n_seg, pos_capacity);
-  *list_offset = w.off_plist;
-  *cursor_offset = w.off_cursor;
-  return DML_OK;
-}
-
-static int rank_segments_impl(const float* values, const float* minmax, int32_t minmax_slot, float* conf_out,
-                              const uint8_t* gt_u8, const int64_t* gt_i64, uint64_t out_label_mask, const uint8_t* pos_u8,
-                              int32_t score_kind, uint32_t key_base, int32_t n_seg, int64_t seg_len, uint32_t* keys_out,
-                              long long* seg_stats, const float* msp, float* msp_norm_out, float* mix_out, float lambda,
-                              float thr, int32_t pos_capacity, double recall_level, void* workspace, size_t workspace_bytes,
-                              dml_ood_result* results, int32_t positives_ready, dml_stream_t stream_) {
+int dml_ood_rank_segments(const float* values, const float* minmax, int32_t minmax_slot, float* conf_out,
+                          const uint8_t* gt_u8, const int64_t* gt_i64, uint64_t out_label_mask, const uint8_t* pos_u8,
+                          int32_t score_kind, uint32_t key_base, int32_t n_seg, int64_t seg_len, uint32_t* keys_out,
+                          long long* seg_stats, const float* msp, float* msp_norm_out, float* mix_out, float lambda,
+                          float thr, int32_t pos_capacity, double recall_level, void* workspace, size_t workspace_bytes,
+                          dml_ood_result* results, dml_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (!values || !seg_stats || !workspace || !results || n_seg < 0 || seg_len < 0 || n_seg > 65535) return DML_ERR_INVALID_ARG;
   if (seg_len >= (1ll << 32)) return DML_ERR_INVALID_ARG;
@@ -612,11 +593,11 @@ static int rank_segments_impl(const float* values, const float* minmax, int32_t 
   uint32_t* cursor = reinterpret_cast<uint32_t*>(ws + w.off_cursor);
   unsigned long long* st = (unsigned long long*)seg_stats;
   DML_CUDA_TRY(cudaMemsetAsync(seg_stats, 0, (size_t)n_seg * 4 * sizeof(long long), stream));
-  if (!positives_ready) DML_CUDA_TRY(cudaMemsetAsync(cursor, 0, (size_t)n_seg * sizeof(uint32_t), stream));
+  DML_CUDA_TRY(cudaMemsetAsync(cursor, 0, (size_t)n_seg * sizeof(uint32_t), stream));
   const long long* g64 = (const long long*)gt_i64;
 
-  // 1. positives (positives_ready: the producer of `values` already appended them, raw, to the workspace's list)
-  if (seg_len > 0 && !positives_ready) {
+  // 1. positives
+  if (seg_len > 0) {
     long long bx = (seg_len / 16 + 255) / 256;
     // one resident wave (4 CTAs of 256 threads per SM): a partial second wave would cost a whole wave's time
     const long long capb = n_seg >= 148 * 4 ? 1 : (148 * 4) / n_seg;
@@ -639,8 +620,7 @@ static int rank_segments_impl(const float* values, const float* minmax, int32_t 
     const size_t smem = (size_t)n2 * sizeof(uint32_t) + (size_t)(BUCKET_SORT_NB + 1) * sizeof(uint32_t) +
                         (size_t)BUCKET_SORT_MAX * sizeof(unsigned short) + 16;
     DML_CUDA_TRY(cudaFuncSetAttribute(pos_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    pos_sort_kernel<<<n_seg, RANK_THREADS, smem, stream>>>(plist, cursor, pos_capacity, key_base, S, pc, cnt, G, st, minmax, minmax_slot,
-                                                           score_kind, positives_ready ? 1 : 0);
+    pos_sort_kernel<<<n_seg, RANK_THREADS, smem, stream>>>(plist, cursor, pos_capacity, key_base, S, pc, cnt, G, st);
     DML_LAUNCH_CHECK();
   }
   // 3. rank
@@ -682,28 +662,6 @@ static int rank_segments_impl(const float* values, const float* minmax, int32_t 
   rank_scan_kernel<<<n_seg, RANK_THREADS, 0, stream>>>(pc, cnt, G, pos_capacity, seg_len, st, recall_level, results);
   DML_LAUNCH_CHECK();
   return DML_OK;
-}
-
-int dml_ood_rank_segments(const float* values, const float* minmax, int32_t minmax_slot, float* conf_out,
-                          const uint8_t* gt_u8, const int64_t* gt_i64, uint64_t out_label_mask, const uint8_t* pos_u8,
-                          int32_t score_kind, uint32_t key_base, int32_t n_seg, int64_t seg_len, uint32_t* keys_out,
-                          long long* seg_stats, const float* msp, float* msp_norm_out, float* mix_out, float lambda,
-                          float thr, int32_t pos_capacity, double recall_level, void* workspace, size_t workspace_bytes,
-                          dml_ood_result* results, dml_stream_t stream) {
-  return rank_segments_impl(values, minmax, minmax_slot, conf_out, gt_u8, gt_i64, out_label_mask, pos_u8, score_kind, key_base, n_seg,
-                            seg_len, keys_out, seg_stats, msp, msp_norm_out, mix_out, lambda, thr, pos_capacity, recall_level, workspace,
-                            workspace_bytes, results, 0, stream);
-}
-
-int dml_ood_rank_segments_pregathered(const float* values, const float* minmax, int32_t minmax_slot, float* conf_out,
-                                      const uint8_t* gt_u8, const int64_t* gt_i64, uint64_t out_label_mask, const uint8_t* pos_u8,
-                                      int32_t score_kind, uint32_t key_base, int32_t n_seg, int64_t seg_len, uint32_t* keys_out,
-                                      long long* seg_stats, const float* msp, float* msp_norm_out, float* mix_out, float lambda,
-                                      float thr, int32_t pos_capacity, double recall_level, void* workspace, size_t workspace_bytes,
-                                      dml_ood_result* results, dml_stream_t stream) {
-  return rank_segments_impl(values, minmax, minmax_slot, conf_out, gt_u8, gt_i64, out_label_mask, pos_u8, score_kind, key_base, n_seg,
-                            seg_len, keys_out, seg_stats, msp, msp_norm_out, mix_out, lambda, thr, pos_capacity, recall_level, workspace,
-                            workspace_bytes, results, 1, stream);
 }
 
 int dml_ood_rank_export_positives(const void* rank_workspace, size_t workspace_bytes, int32_t n_seg, int32_t pos_capacity,

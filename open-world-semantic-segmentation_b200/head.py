@@ -56,7 +56,7 @@ def dml_head(x: torch.Tensor, centers: Optional[torch.Tensor] = None, magnitude:
              novel_thr: float = NOVEL_THRESHOLD, want_novel_dist: bool = False,
              gt: Optional[torch.Tensor] = None, confusion: Optional[torch.Tensor] = None,
              confusion_shape: Optional[tuple] = None, out: Optional[HeadOutput] = None,
-             reference_order: bool = False, positives=None) -> HeadOutput:
+             reference_order: bool = False) -> HeadOutput:
     """One pass over ``x`` [B,D,H,W] (fp32, CUDA, contiguous NCHW).
 
     input_is_logits: ``x`` already holds the logits z [B,K,H,W] (anomaly path: stride-8 distances
@@ -72,9 +72,6 @@ def dml_head(x: torch.Tensor, centers: Optional[torch.Tensor] = None, magnitude:
     reference_order: parity mode (``centers`` = m*I, D < 16, logits requested): every logit is rounded exactly like
              the reference's torch-CPU op sequence (anomaly/models/models.py:649-651), so the logits -- and everything
              derived from them -- are bit-identical to the reference's on identical embeddings.
-    positives: an ``ood.PositiveList`` (needs ``gt``): the raw EDS value of every pixel whose label is in its
-             ``out_labels`` is appended to the list while it is in registers, so that
-             ``ood.eval_segments(eds, ..., method="rank", positives=pl)`` skips its gather pass over the label map.
     """
     require_cuda(x, "x")
     if x.dtype != torch.float32 or x.dim() != 4:
@@ -171,14 +168,6 @@ def dml_head(x: torch.Tensor, centers: Optional[torch.Tensor] = None, magnitude:
             p.gt_u8 = gt.data_ptr()
         else:
             p.gt_i64 = gt.data_ptr()
-    if positives is not None:
-        if gt is None:
-            raise ValueError("positives needs gt")
-        if positives.n_seg != B or positives.rws.device != dev:
-            raise ValueError("positives: PositiveList built for another batch size / device")
-        from .ood import label_mask
-        p.pos_values, p.pos_cursor = positives.values.data_ptr(), positives.cursor.data_ptr()
-        p.pos_capacity, p.pos_label_mask = positives.pos_capacity, label_mask(positives.out_labels)
     with torch.cuda.device(dev):
         check(lib().dml_head_forward(C.byref(p), stream_ptr(dev)), "dml_head_forward")
     return o

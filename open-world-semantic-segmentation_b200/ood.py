@@ -54,27 +54,6 @@ class OodWorkspace:
         return cur
 
 
-class PositiveList:
-    """The positives' list of ONE ``eval_segments(..., method="rank")`` batch, filled by the kernel that produces the
-    scores instead of by a gather pass over the label map: hand it to ``head.dml_head(..., gt=gt, positives=pl)`` (the
-    head appends the raw EDS value of every pixel whose label is in ``out_labels`` while the value is in registers) and
-    then to ``eval_segments(eds, ..., method="rank", positives=pl)`` with the same ``n_seg`` / ``pos_capacity``.
-    The list lives in the rank workspace; creating the object zeroes its per-segment cursors (one small memset)."""
-
-    def __init__(self, workspace: "OodWorkspace", n_seg: int, out_labels: Sequence[int] = (13,),
-                 pos_capacity: int = POS_CAPACITY_DEFAULT):
-        self.n_seg = int(n_seg)
-        self.pos_capacity = int(min(max(pos_capacity, 1), 32768))
-        self.out_labels = tuple(int(v) for v in out_labels)
-        self.rws = workspace.get("rank_ws", lib().dml_ood_rank_workspace_bytes(self.n_seg, self.pos_capacity))
-        lo, co = C.c_size_t(), C.c_size_t()
-        check(lib().dml_ood_rank_workspace_layout(self.n_seg, self.pos_capacity, C.byref(lo), C.byref(co)),
-              "dml_ood_rank_workspace_layout")
-        self.values = self.rws[lo.value: lo.value + 4 * self.n_seg * self.pos_capacity].view(torch.int32)
-        self.cursor = self.rws[co.value: co.value + 4 * self.n_seg].view(torch.int32)
-        self.cursor.zero_()
-
-
 class KeyPool:
     """Pooled metric over the (score, label) pairs of many ``eval_segments`` calls -- e.g. the exact full-set
     AUROC / AUPR / FPR@95 next to the per-image mean -- without generating or counting the ranking keys twice.
@@ -165,7 +144,7 @@ def eval_segments(values: torch.Tensor, n_seg: int, seg_len: int, *, gt: Optiona
                   workspace: Optional[OodWorkspace] = None, msp: Optional[torch.Tensor] = None,
                   msp_norm_out: Optional[torch.Tensor] = None, mix_out: Optional[torch.Tensor] = None,
                   lam: float = 50.0, thr: float = 0.2, pool: Optional[KeyPool] = None, method: str = "sort",
-                  pos_capacity: int = POS_CAPACITY_DEFAULT, positives: Optional[PositiveList] = None):
+                  pos_capacity: int = POS_CAPACITY_DEFAULT):
     """Evaluate ``n_seg`` independent segments of ``seg_len`` (score, label) pairs each.
 
     values: flat fp32 CUDA tensor (n_seg*seg_len): a ``conf`` map ranked as score = -conf
@@ -186,8 +165,6 @@ def eval_segments(values: torch.Tensor, n_seg: int, seg_len: int, *, gt: Optiona
             re-evaluation with "sort" if any is set (the inputs must still be intact, so not for in-place pipelines).
             AUROC / FPR are bit-identical between the methods, AUPR differs by float64 summation order;
             ``results[:, 6]`` (n_groups) is -1 on the rank path.
-    positives: (method "rank" / "auto") a ``PositiveList`` the producer of ``values`` already filled (``head.dml_head(...,
-            positives=pl)``): the gather pass over the label map is skipped.
     Returns (results, stats): device tensors -- results float64 [n_seg,7] viewed as
     (auroc, aupr, fpr, n_pos, n_neg, n_nan, n_groups; the last four are int64 bit patterns),
     stats int64 [n_seg,4] = (n_pos, n_nan, n_out_of_window, 0).  No host synchronisation.
@@ -203,10 +180,7 @@ def eval_segments(values: torch.Tensor, n_seg: int, seg_len: int, *, gt: Optiona
     n = n_seg * seg_len
     if method != "sort" and n > 0:
         return _eval_segments_rank(values, n_seg, seg_len, gt, out_labels, positive, score_kind, key_base, minmax, minmax_slot,
-                                   conf_out, recall_level, ws, msp, msp_norm_out, mix_out, lam, thr, pool, method, pos_capacity,
-                                   positives)
-    if positives is not None:
-        raise ValueError("positives belongs to method='rank' / 'auto'")
+                                   conf_out, recall_level, ws, msp, msp_norm_out, mix_out, lam, thr, pool, method, pos_capacity)
     keys = ws.get("keys", 4 * n) if pool is None else pool._take(n, (int(key_base), int(score_kind)))
     stats = ws.get("stats", 32 * max(n_seg, 1)).view(torch.int64)[: 4 * n_seg].view(n_seg, 4)
     results = ws.get("results", 8 * OOD_RESULT_WORDS * max(n_seg, 1)).view(torch.float64)[: OOD_RESULT_WORDS * n_seg]
@@ -281,7 +255,7 @@ def _labels_of(gt, positive, n):
 
 
 def _eval_segments_rank(values, n_seg, seg_len, gt, out_labels, positive, score_kind, key_base, minmax, minmax_slot, conf_out,
-                        recall_level, ws, msp, msp_norm_out, mix_out, lam, thr, pool, method, pos_capacity, positives=None):
+                        recall_level, ws, msp, msp_norm_out, mix_out, lam, thr, pool, method, pos_capacity):
     """``eval_segments`` through ``dml_ood_rank_segments`` (see there)."""
     dev = values.device
     n = n_seg * seg_len
@@ -290,25 +264,16 @@ def _eval_segments_rank(values, n_seg, seg_len, gt, out_labels, positive, score_
     stats = ws.get("stats", 32 * max(n_seg, 1)).view(torch.int64)[: 4 * n_seg].view(n_seg, 4)
     results = ws.get("results", 8 * OOD_RESULT_WORDS * max(n_seg, 1)).view(torch.float64)[: OOD_RESULT_WORDS * n_seg]
     results = results.view(n_seg, OOD_RESULT_WORDS)
-    if positives is not None:
-        if positives.n_seg != n_seg or positives.pos_capacity != pos_capacity or positives.rws.device != dev:
-            raise ValueError("positives: PositiveList built for another n_seg / pos_capacity / device")
-        if positive is not None or tuple(int(v) for v in out_labels) != positives.out_labels:
-            raise ValueError("positives: the list was gathered for other labels")
-        rws = positives.rws
-        entry, entry_name = lib().dml_ood_rank_segments_pregathered, "dml_ood_rank_segments_pregathered"
-    else:
-        rws = ws.get("rank_ws", lib().dml_ood_rank_workspace_bytes(n_seg, pos_capacity))
-        entry, entry_name = lib().dml_ood_rank_segments, "dml_ood_rank_segments"
+    rws = ws.get("rank_ws", lib().dml_ood_rank_workspace_bytes(n_seg, pos_capacity))
     pool_mark = (pool.n, pool.signature, pool.hist_ok) if pool is not None else None
     keys = pool._take(n, (int(key_base), int(score_kind))) if pool is not None else None
     with torch.cuda.device(dev):
         s = stream_ptr(dev)
-        check(entry(ptr(values), ptr(minmax), minmax_slot, ptr(conf_out), ptr(gt_u8), ptr(gt_i64),
+        check(lib().dml_ood_rank_segments(ptr(values), ptr(minmax), minmax_slot, ptr(conf_out), ptr(gt_u8), ptr(gt_i64),
                                           label_mask(out_labels) if positive is None else 0, ptr(pos_u8), score_kind,
                                           key_base, n_seg, seg_len, ptr(keys), ptr(stats), ptr(msp), ptr(msp_norm_out),
                                           ptr(mix_out), lam, thr, pos_capacity, recall_level, ptr(rws), rws.numel(),
-                                          ptr(results), s), entry_name)
+                                          ptr(results), s), "dml_ood_rank_segments")
         if method == "auto" and bool((stats[:, 3] != 0).any().item()):       # the one host synchronisation of "auto"
             if pool is not None:
                 pool.n, pool.signature, pool.hist_ok = pool_mark

@@ -277,48 +277,3 @@ def test_rank_error_behaviour_and_plain_scores():
         out[m], _ = ood.results_to_host(r, t)
     assert out["rank"][0, 0] == out["sort"][0, 0] and out["rank"][0, 2] == out["sort"][0, 2]
     np.testing.assert_allclose(out["rank"][0], O.get_measures(score[gt == 13], score[gt != 13]), atol=1e-12)
-
-
-@pytest.mark.parametrize("gt_dtype", [torch.uint8, torch.int64])
-@pytest.mark.parametrize("shape", [(5, 13, 96, 160), (3, 13, 37, 53), (2, 17, 64, 64)])
-def test_positives_gathered_by_the_head(gt_dtype, shape):
-    """head.dml_head(positives=pl) + eval_segments(positives=pl) == the separate gather pass, bit for bit (the list order
-    differs, the sorted list does not); an overflowing image is flagged the same way"""
-    from dml_b200 import head as H, ood
-    B, K, Hh, Ww = shape
-    rng = np.random.default_rng(B * 100 + Ww)
-    gt_np = rng.integers(0, K, (B, Hh, Ww))
-    gt_np[rng.random((B, Hh, Ww)) < 0.03] = K                                # OOD label = K
-    gt_np[0, :2] = K                                                         # two full rows in image 0
-    x = torch.from_numpy((rng.standard_normal((B, K, Hh, Ww)) * 0.7).astype(np.float32)).cuda()
-    gt = torch.from_numpy(gt_np).to(gt_dtype).cuda()
-    outs = {}
-    for fused in (False, True):
-        for cap in (16384, 64):                                              # 64: every image overflows
-            ws = ood.OodWorkspace(x.device)
-            pl = ood.PositiveList(ws, B, out_labels=(K,), pos_capacity=cap) if fused else None
-            o = H.dml_head(x, magnitude=3.0, want_logits=False, want_eds=True, eds_clamp=400.0, want_msp=True, want_minmax=True,
-                           gt=gt, positives=pl)
-            pool = ood.KeyPool(B * Hh * Ww, x.device, histograms=False)
-            res, st = ood.eval_segments(o.eds, B, Hh * Ww, gt=gt, out_labels=(K,), minmax=o.minmax, workspace=ws, method="rank",
-                                        pos_capacity=cap, positives=pl, pool=pool)
-            outs[(fused, cap)] = (res.cpu().numpy().copy(), st.cpu().numpy().copy(), int(pool.pos_count.item()),
-                                  np.sort(pool.pos[: int(pool.pos_count.item())].cpu().numpy()))
-    for cap in (16384, 64):
-        a, b = outs[(False, cap)], outs[(True, cap)]
-        np.testing.assert_array_equal(a[0].view(np.uint64), b[0].view(np.uint64))
-        np.testing.assert_array_equal(a[1], b[1])
-        assert a[2] == b[2]
-        np.testing.assert_array_equal(a[3], b[3])
-    assert (outs[(True, 64)][1][:, 3] == 1).all() and (outs[(True, 16384)][1][:, 3] == 0).all()
-    # and against the oracle
-    vals, _ = ood.results_to_host(torch.from_numpy(outs[(True, 16384)][0]), torch.from_numpy(outs[(True, 16384)][1]))
-    o = H.dml_head(x, magnitude=3.0, want_logits=False, want_eds=True, eds_clamp=400.0, want_minmax=True)
-    eds = o.eds.cpu().numpy()
-    for b in range(B):
-        e = eds[b].ravel()
-        conf = ((e - e.min()) / (e.max() - e.min())).astype(np.float32)
-        np.testing.assert_allclose(vals[b, :3], O.eval_ood_measure(conf, gt_np[b].ravel(), (K,)), atol=1e-12)
-    with pytest.raises(ValueError):
-        ood.eval_segments(o.eds, B, Hh * Ww, gt=gt, out_labels=(K,), minmax=o.minmax, method="sort",
-                          positives=ood.PositiveList(ood.OodWorkspace(x.device), B, out_labels=(K,)))

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     assert len(names) >= 20
     for n in names:
         assert hasattr(lib, n), f"libdml_b200.so does not export {n}"
-    assert lib.dml_abi_version() == 5
+    assert lib.dml_abi_version() == 4
     assert lib.dml_max_dim() == 32
     assert lib.dml_error_string(-2).decode().startswith("embedding dim")
 
