@@ -599,7 +599,8 @@ int dml_ood_rank_segments(const float* values, const float* minmax, int32_t minm
   // 1. positives
   if (seg_len > 0) {
     long long bx = (seg_len / 16 + 255) / 256;
-    // one resident wave (4 CTAs of 256 threads per SM): a partial second wave would cost a whole wave's time
+    // one resident wave (4 CTAs of 256 threads per SM): a partial second wave would cost a whole wave's time, and 8 or 16
+    // CTAs per SM measured slower (per-image stage 13.08 / 13.18 / 13.22 ms per 1500 images)
     const long long capb = n_seg >= 148 * 4 ? 1 : (148 * 4) / n_seg;
     if (bx > capb) bx = capb;
     if (bx < 1) bx = 1;
