@@ -108,20 +108,20 @@ __global__ void __launch_bounds__(LOSS_THREADS) loss_kernel(const LossArgs a) {
       // exact difference of embeddings (x_ext = max x for m > 0, min x for m < 0); dense: from the distances.
       float zk[DENSE ? DML_MAX_DIM : 1];  // dense: logits kept for the second sweep
       float ext = 0.f, dy = 0.f, dsum = 0.f;
-      int kext = 0;
+      [[maybe_unused]] int kext = 0;   // dense prototypes only
       if constexpr (IDENT) {
+        // only the VALUE of the extremal channel is needed (one min/max per class): the classes that attain it -- normally
+        // one -- are recognised below by x_k == x_ext, so no index has to be tracked through the loop
+        const bool up = two_m >= 0.f;
         ext = x[0][v];
 #pragma unroll
-        for (int k = 1; k < D; ++k) {
-          const bool better = two_m >= 0.f ? (x[k][v] > ext) : (x[k][v] < ext);
-          if (better) { ext = x[k][v]; kext = k; }
-        }
+        for (int k = 1; k < D; ++k) ext = up ? fmaxf(ext, x[k][v]) : fminf(ext, x[k][v]);
       } else if constexpr (LOGITS) {
         ext = x[0][v];
         dsum = -x[0][v];
 #pragma unroll
         for (int k = 1; k < D; ++k) {
-          if (x[k][v] > ext) { ext = x[k][v]; kext = k; }
+          ext = fmaxf(ext, x[k][v]);
           dsum -= x[k][v];
         }
       } else {
@@ -145,13 +145,24 @@ __global__ void __launch_bounds__(LOSS_THREADS) loss_kernel(const LossArgs a) {
       // r = sum_{k != kext} exp(u_k); the extremal term is exactly 1 and is kept out of the sum so that
       // log1p(r) stays accurate for well-separated pixels.  uy = u_y.
       float r = 0.f, uy = 0.f;
+      [[maybe_unused]] float xy = 0.f;   // x_y (IDENT / LOGITS)
+      // exp(u_k) = 2^(c x_k - c x_ext), c = scale log2(e): one FMA + one MUFU per class (the subtract-scale-scale form
+      // cost three dependent multiplies / adds); the target's channel is picked once and u_y formed from it after the loop
+      [[maybe_unused]] const float sc = LOGITS ? 1.0f : two_m;
+      [[maybe_unused]] const float c = sc * LOG2E;
+      [[maybe_unused]] const float nce = -c * ext;
       if constexpr (IDENT || LOGITS) {
+        int n0 = 0;                      // classes at the extremum: their terms are exactly 1; all but one enter r
 #pragma unroll
         for (int k = 0; k < D; ++k) {
-          const float u = (LOGITS ? 1.0f : two_m) * (x[k][v] - ext);
-          if (k == y) { uy = u; if (LOGITS) dy = -x[k][v]; }
-          if (k != kext) r += ex2_approx(u * LOG2E);
+          const float xk = x[k][v];
+          const float e = ex2_approx(fmaf(c, xk, nce));
+          if (k == y) xy = xk;
+          if (xk == ext) ++n0; else r += e;
         }
+        r += (float)(n0 - 1);
+        uy = sc * (xy - ext);
+        if constexpr (LOGITS) dy = -xy;
       } else {
 #pragma unroll
         for (int k = 0; k < DML_MAX_DIM; ++k)
@@ -166,13 +177,13 @@ __global__ void __launch_bounds__(LOSS_THREADS) loss_kernel(const LossArgs a) {
           if constexpr (IDENT) {
             // d_y = sum_{d != y} x_d^2 + (x_y - m)^2 (positive terms only);
             // sum_k d_k = K ||x||^2 - 2m sum_k x_k + K m^2 (large, only feeds Inter)
-            float xy = 0.f, loo = 0.f, sx = 0.f, sumsq = 0.f;
+            float loo = 0.f, sx = 0.f;
 #pragma unroll
             for (int k = 0; k < D; ++k) {
-              if (k == y) xy = x[k][v]; else loo = fmaf(x[k][v], x[k][v], loo);
-              sumsq = fmaf(x[k][v], x[k][v], sumsq);
+              if (k != y) loo = fmaf(x[k][v], x[k][v], loo);
               sx += x[k][v];
             }
+            const float sumsq = fmaf(xy, xy, loo);      // ||x||^2 = the leave-one-out sum + x_y^2 (positive terms: no cancellation)
             const float ty_m = xy - a.diag_m;
             dy = fmaf(ty_m, ty_m, loo);
             dsum = (float)D * sumsq - two_m * sx + (float)D * a.diag_m * a.diag_m;
@@ -190,7 +201,7 @@ __global__ void __launch_bounds__(LOSS_THREADS) loss_kernel(const LossArgs a) {
         if constexpr (IDENT || LOGITS) {
 #pragma unroll
           for (int d = 0; d < D; ++d) {
-            const float pk = (d == kext ? 1.0f : ex2_approx((LOGITS ? 1.0f : two_m) * (x[d][v] - ext) * LOG2E)) * inv_s;
+            const float pk = (x[d][v] == ext ? 1.0f : ex2_approx(fmaf(c, x[d][v], nce))) * inv_s;
             const float oh = (d == y) ? 1.f : 0.f;
             const float gk = gscale * ((pk - oh) * inv_nv - a_t * oh + b_t * (1.f - oh));
             const float g = LOGITS ? gk : -2.0f * (G * x[d][v] - a.diag_m * gk);
