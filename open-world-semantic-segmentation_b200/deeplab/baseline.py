@@ -37,5 +37,8 @@ def roc_measures(scores: torch.Tensor, labels: torch.Tensor, labels_true: Option
     pos = lab == ood_label
     if s.numel() == 0 or not bool(pos.any()):
         return None
+    if bool(pos.all()):
+        # every evaluated pixel is positive: sklearn's roc_auc_score (test.py:241) raises here
+        raise ValueError("Only one class present in y_true. ROC AUC score is not defined in that case.")
     return ood.measures_from_scores(s.contiguous(), pos, recall_level=recall_level, workspace=workspace,
                                     fpr_convention="roc_curve")

@@ -92,3 +92,12 @@ def test_baseline_evaluator_drop_in():
     got = baseline.roc_measures(torch.from_numpy(ref_scores).cuda(), labels.cuda(), labels_true.cuda())
     np.testing.assert_allclose(got, ref, rtol=0, atol=1e-12)
     assert baseline.roc_measures(scores, torch.zeros_like(labels).cuda(), labels_true.cuda()) is None
+
+
+def test_single_class_input_raises_like_sklearn():
+    from dml_b200.deeplab import baseline as B
+    s = torch.rand(64, device="cuda")
+    lab = torch.full((64,), 255, dtype=torch.int64, device="cuda")
+    with pytest.raises(ValueError, match="Only one class"):
+        B.roc_measures(s, lab)
+    assert B.roc_measures(s, torch.zeros(64, dtype=torch.int64, device="cuda")) is None        # test.py:224: no positive pixel
