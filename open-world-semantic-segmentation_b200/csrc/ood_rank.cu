@@ -371,7 +371,7 @@ __global__ void __launch_bounds__(RANK_THREADS, 1) rank_kernel(const float* __re
             mn[j] = apply_norm(nmm, m[j]);
             // NumPy: c = 1 / (1 + exp(lamda * (e - thre))); mix = c*e + (1-c)*mmsp   (float32)
             // (1 / x correctly rounded == IEEE 1.0f / x: the reciprocal sequence is half the division subroutine)
-            const float c = __frcp_rn(__fadd_rn(1.0f, expf(__fmul_rn(fz.lambda, __fsub_rn(v[j], fz.thr)))));
+            const float c = mix_coefficient_fast(v[j], fz.lambda, fz.thr);
             mx[j] = __fadd_rn(__fmul_rn(c, v[j]), __fmul_rn(__fsub_rn(1.0f, c), mn[j]));
           }
           if constexpr (VEC == 4) {

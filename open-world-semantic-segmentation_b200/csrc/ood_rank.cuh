@@ -15,6 +15,19 @@ __device__ __forceinline__ float key_float(uint32_t skey, uint32_t key_base) {
   return __uint_as_float(u);
 }
 
+// EDS / MMSP mix coefficient 1 / (1 + exp(lambda (conf - thr))) (anomaly/eval_ood_traditional.py:101-106) for the one-pass
+// rank kernel, which is issue-bound: exp as ex2.approx of the scaled argument, reciprocal as rcp.approx -- 4 instructions
+// instead of ~20 for expf + IEEE reciprocal.  The coefficient is within 7e-7 (absolute) of the correctly rounded one
+// (argument rounding at |lambda (conf - thr)| <= 40 dominates: 2.6e-6 relative on exp, times c (1 - c) <= 1/4), the mix map
+// within the same bound: inside the 1e-5 bar, but no longer bit-identical to dml_ood_keygen / dml_scores_finalize, which keep
+// the IEEE forms.  exp = inf gives 0 and exp = 0 gives 1 like the reference's float32 arithmetic.
+__device__ __forceinline__ float mix_coefficient_fast(float v, float lambda, float thr) {
+  const float e = ex2_approx(__fmul_rn(__fmul_rn(lambda, __fsub_rn(v, thr)), 1.4426950408889634f));
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(__fadd_rn(1.0f, e)));
+  return r;
+}
+
 // per-segment normalisation constants, as dml_ood_keygen applies them: NumPy's fp32 (x - min) / (max - min).
 // The divisor is constant per segment, so the IEEE division is evaluated as Markstein's sequence on the correctly
 // rounded reciprocal r = RN(1 / den):  q0 = x r;  rem = fma(-q0, den, x) (exact);  q = fma(rem, r, q0)  ==  RN(x / den)
