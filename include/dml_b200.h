@@ -203,7 +203,7 @@ DML_API int dml_conv1x1_head_forward(const float* features, const float* weight,
  *   DeepLabV3Plus-Pytorch/utils/loss.py:34-82 (line 79 form; shipped early return = alpha=beta=0)
  *   loss = (CE + alpha*VL + beta*Inter)/n  -- see SURVEY.md appendix A.6.
  * Forward writes 4 doubles: loss, CE, VL, Inter and the valid-pixel count as double in [4].
- * `partials` is a workspace of dml_loss_workspace_bytes(B,H,W).
+ * `partials` is a 16-byte aligned workspace of dml_loss_workspace_bytes(B,H,W).
  * Backward recomputes the distances and writes dL/dx [B,D,H,W] scaled by *grad_out (device scalar).
  * x_is_logits != 0: `x` already holds the logits z [B,K,H,W] (the reference criterion's signature,
  * utils/loss.py:34 `forward(logit, target, features_in)`); mu must be NULL and dx is dL/dz.
