@@ -538,19 +538,25 @@ __global__ void __launch_bounds__(RANK_THREADS) rank_scan_kernel(const uint32_t*
 }
 
 // positives of every segment of the last dml_ood_rank_segments call -> appended to one list (pooled metric)
+constexpr int EXPORT_SPLIT = 8;
 __global__ void __launch_bounds__(256) export_positives_kernel(const uint32_t* __restrict__ plist, const uint32_t* __restrict__ cursor,
                                                                int cap, uint32_t* __restrict__ out, long long out_capacity,
                                                                unsigned long long* __restrict__ count) {
+  // EXPORT_SPLIT CTAs per segment (one CTA copied its ~9000 keys with a single load in flight per thread: 18 us per batch);
+  // each reserves its own piece of the output list -- the order of the list is irrelevant
   __shared__ unsigned long long s_base;
   const int seg = blockIdx.x;
   const uint32_t np_all = cursor[seg];
   const uint32_t P = np_all > (uint32_t)cap ? 0u : np_all;   // an overflowed segment exports nothing: the count then falls short
-  if (threadIdx.x == 0) s_base = atomicAdd(count, (unsigned long long)P);
+  const uint32_t piece = (P + EXPORT_SPLIT - 1) / EXPORT_SPLIT;
+  const uint32_t i0 = min(blockIdx.y * piece, P), i1 = min(i0 + piece, P);
+  if (i0 == i1) return;
+  if (threadIdx.x == 0) s_base = atomicAdd(count, (unsigned long long)(i1 - i0));
   __syncthreads();
   const unsigned long long base = s_base;
-  if (base + P > (unsigned long long)out_capacity) return;
-  const uint32_t* src = plist + (size_t)seg * cap;
-  for (uint32_t i = threadIdx.x; i < P; i += blockDim.x) out[base + i] = src[i];
+  if (base + (i1 - i0) > (unsigned long long)out_capacity) return;
+  const uint32_t* src = plist + (size_t)seg * cap + i0;
+  for (uint32_t i = threadIdx.x; i < i1 - i0; i += blockDim.x) out[base + i] = src[i];
 }
 
 }  // namespace
@@ -673,7 +679,7 @@ int dml_ood_rank_export_positives(const void* rank_workspace, size_t workspace_b
   const RankWs w = make_rank_ws(n_seg, pos_capacity);
   if (workspace_bytes < w.off_end) return DML_ERR_WORKSPACE;
   const unsigned char* ws = reinterpret_cast<const unsigned char*>(rank_workspace);
-  export_positives_kernel<<<n_seg, 256, 0, stream>>>(reinterpret_cast<const uint32_t*>(ws + w.off_plist),
+  export_positives_kernel<<<dim3((unsigned)n_seg, EXPORT_SPLIT), 256, 0, stream>>>(reinterpret_cast<const uint32_t*>(ws + w.off_plist),
                                                      reinterpret_cast<const uint32_t*>(ws + w.off_cursor), pos_capacity, out,
                                                      out_capacity, (unsigned long long*)count);
   DML_LAUNCH_CHECK();
