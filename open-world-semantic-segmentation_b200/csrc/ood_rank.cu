@@ -7,8 +7,9 @@
 //   decided at positive groups and the negative-only groups right after them.
 // OOD pixels are rare (~1 % of an image), so instead of radix-sorting every (score, label) pair (4 passes x 8 B / pair,
 // issue-bound at ~35 % of HBM) this path
-//   1. gathers the positives' packed keys per segment                      (pos_gather_kernel: reads gt, 1 B / pair)
-//   2. sorts + de-duplicates them, one CTA per segment in shared memory    (pos_sort_kernel: S[g], pc[g])
+//   1. gathers the positives' pixel indices per segment                    (pos_gather_kernel: reads gt, 1 B / pair)
+//   2. fetches their values, normalises + packs the keys, sorts + de-duplicates them, one CTA per segment in shared
+//      memory                                                              (pos_sort_kernel: S[g], pc[g])
 //   3. streams over all pairs ONCE: normalisation, conf / MMSP / mix maps, packed keys for the pooled metric, and for
 //      every negative a lower_bound in the segment's S (value-linear LUT + a few probes, all in shared memory) followed
 //      by one shared-memory counter increment                              (rank_kernel: replaces key-gen + 4 sort
@@ -46,19 +47,19 @@ RankWs make_rank_ws(int n_seg, int cap) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// 1. positives -> per-segment list of packed score keys (key >> 1), any order
+// 1. positives -> per-segment list of their pixel indices, any order
 // ---------------------------------------------------------------------------------------------
+// The list holds pixel INDICES (within the segment); pos_sort_kernel turns them into keys.  Keeping the sparse value loads
+// out of this kernel leaves a pure scan of the label map: 32 labels per thread and step (two 16-byte loads in flight),
+// one ballot, and -- for the few warps that see a positive -- one cursor reservation.
 template <typename GT>
-__global__ void __launch_bounds__(256) pos_gather_kernel(const float* __restrict__ values, const float* __restrict__ minmax, int slot,
-                                                         const GT* __restrict__ gt, uint64_t out_mask,
-                                                         const uint8_t* __restrict__ pos_u8, int kind, long long seg_len,
-                                                         uint32_t key_base, int cap, uint32_t* __restrict__ plist,
-                                                         uint32_t* __restrict__ cursor) {
+__global__ void __launch_bounds__(256) pos_gather_kernel(const GT* __restrict__ gt, uint64_t out_mask,
+                                                         const uint8_t* __restrict__ pos_u8, long long seg_len, int cap,
+                                                         uint32_t* __restrict__ plist, uint32_t* __restrict__ cursor) {
   const int seg = blockIdx.y;
   const size_t base = (size_t)seg * (size_t)seg_len;
-  const Norm nm = load_norm(minmax, seg, slot);
   const int lane = threadIdx.x & 31;
-  constexpr int PER = 16;   // consecutive pixels per thread and step
+  constexpr int PER = 32;   // consecutive pixels per thread and step
   const bool bytes = pos_u8 != nullptr || sizeof(GT) == 1;
   const uint8_t* gb = pos_u8 ? pos_u8 : reinterpret_cast<const uint8_t*>(gt);
   const bool vec_ok = bytes && (seg_len % PER == 0) && ((reinterpret_cast<uintptr_t>(gb) & 15) == 0);
@@ -66,17 +67,16 @@ __global__ void __launch_bounds__(256) pos_gather_kernel(const float* __restrict
   const long long stride = (long long)gridDim.x * blockDim.x;
   const long long q_end = ((nstep + stride - 1) / stride) * stride;   // block-uniform trip count (warp collectives below)
   uint32_t* out = plist + (size_t)seg * cap;
-  // (four label loads in flight per thread were tried: 97 us instead of 68 per 74 images -- the unrolled per-step code
-  //  costs more than the overlapped latency buys)
   for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < q_end; q += stride) {
     unsigned flags = 0u;
     const long long p0 = q * PER;
     if (q < nstep) {
       if (vec_ok) {
-        const uint4 w = *reinterpret_cast<const uint4*>(gb + base + p0);
-        const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+        const uint4 w0 = *reinterpret_cast<const uint4*>(gb + base + p0);
+        const uint4 w1 = *reinterpret_cast<const uint4*>(gb + base + p0 + 16);
+        const uint32_t ww[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
-        for (int j = 0; j < 4; ++j) flags |= byte_mask_to_bits(positive_bytes(ww[j], out_mask, pos_u8 != nullptr)) << (4 * j);
+        for (int j = 0; j < 8; ++j) flags |= byte_mask_to_bits(positive_bytes(ww[j], out_mask, pos_u8 != nullptr)) << (4 * j);
       } else {
         for (int j = 0; j < PER; ++j) {
           const long long p = p0 + j;
@@ -105,20 +105,11 @@ __global__ void __launch_bounds__(256) pos_gather_kernel(const float* __restrict
     if (lane == 31) wbase = atomicAdd(cursor + seg, (uint32_t)total);
     wbase = __shfl_sync(0xffffffffu, wbase, 31);
     uint32_t dst = wbase + (uint32_t)(incl - c);
-    // all of the thread's (sparse) value loads are issued before the first one is consumed: one memory latency per
-    // step instead of one per positive
-    float vv[PER];
-#pragma unroll
-    for (int j = 0; j < PER; ++j) vv[j] = ((flags >> j) & 1u) ? values[base + p0 + j] : 0.f;
-#pragma unroll
-    for (int j = 0; j < PER; ++j) {
-      if ((flags >> j) & 1u) {
-        if (dst < (uint32_t)cap) {
-          unsigned d0 = 0, d1 = 0;
-          out[dst] = pack_key(apply_norm(nm, vv[j]), kind, true, key_base, d0, d1) >> 1;
-        }
-        ++dst;
-      }
+    while (flags) {
+      const int j = __ffs(flags) - 1;
+      flags &= flags - 1u;
+      if (dst < (uint32_t)cap) out[dst] = (uint32_t)(p0 + j);
+      ++dst;
     }
   }
 }
@@ -130,10 +121,12 @@ __global__ void __launch_bounds__(256) pos_gather_kernel(const float* __restrict
 //    one shared atomic per key, then every bucket (a handful of keys) is insertion-sorted by one thread.
 //    Otherwise: bitonic network over the padded list.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(RANK_THREADS) pos_sort_kernel(const uint32_t* __restrict__ plist, const uint32_t* __restrict__ cursor,
+__global__ void __launch_bounds__(RANK_THREADS) pos_sort_kernel(uint32_t* __restrict__ plist, const uint32_t* __restrict__ cursor,
                                                                 int cap, uint32_t key_base, uint32_t* __restrict__ S,
                                                                 uint32_t* __restrict__ pc, uint32_t* __restrict__ cnt,
-                                                                uint32_t* __restrict__ Gout, unsigned long long* __restrict__ seg_stats) {
+                                                                uint32_t* __restrict__ Gout, unsigned long long* __restrict__ seg_stats,
+                                                                const float* __restrict__ values, const float* __restrict__ minmax,
+                                                                int slot, int kind, long long seg_len) {
   extern __shared__ uint32_t s_k[];                        // [n2(cap)] sorted keys | [NB + 1] bucket offsets | u16 [BUCKET_SORT_MAX] ranks
   __shared__ uint32_t s_w[RANK_THREADS / 32];
   __shared__ uint32_t s_mn, s_mx, s_big;
@@ -150,7 +143,25 @@ __global__ void __launch_bounds__(RANK_THREADS) pos_sort_kernel(const uint32_t* 
   while (n2 < P) n2 <<= 1;
   int n2cap = 2;
   while (n2cap < cap) n2cap <<= 1;
-  const uint32_t* src = plist + (size_t)seg * cap;
+  uint32_t* src = plist + (size_t)seg * cap;
+  {
+    // pixel indices -> normalised, packed score keys, in place (the sparse value loads of a thread are all in flight at once;
+    // the list then also is what dml_ood_rank_export_positives hands to the pooled metric)
+    const Norm nm = load_norm(minmax, seg, slot);
+    const float* vseg = values + (size_t)seg * (size_t)seg_len;
+    for (int i0 = tid; i0 < P; i0 += 8 * RANK_THREADS) {
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { const int i = i0 + u * RANK_THREADS; v[u] = i < P ? vseg[src[i]] : 0.f; }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = i0 + u * RANK_THREADS;
+        unsigned d0 = 0, d1 = 0;
+        if (i < P) src[i] = pack_key(apply_norm(nm, v[u]), kind, true, key_base, d0, d1) >> 1;
+      }
+    }
+    __syncthreads();
+  }
   bool sorted = false;
   if (P > 64 && P <= BUCKET_SORT_MAX) {
     uint32_t* s_off = s_k + n2cap;                                              // [NB + 1]
@@ -604,7 +615,7 @@ int dml_ood_rank_segments(const float* values, const float* minmax, int32_t minm
 
   // 1. positives
   if (seg_len > 0) {
-    long long bx = (seg_len / 16 + 255) / 256;
+    long long bx = (seg_len / 32 + 255) / 256;
     // one resident wave (4 CTAs of 256 threads per SM): a partial second wave would cost a whole wave's time, and 8 or 16
     // CTAs per SM measured slower (per-image stage 13.08 / 13.18 / 13.22 ms per 1500 images)
     const long long capb = n_seg >= 148 * 4 ? 1 : (148 * 4) / n_seg;
@@ -612,11 +623,9 @@ int dml_ood_rank_segments(const float* values, const float* minmax, int32_t minm
     if (bx < 1) bx = 1;
     dim3 grid((unsigned)bx, (unsigned)n_seg);
     if (gt_i64)
-      pos_gather_kernel<long long><<<grid, 256, 0, stream>>>(values, minmax, minmax_slot, g64, out_label_mask, nullptr, score_kind,
-                                                              seg_len, key_base, pos_capacity, plist, cursor);
+      pos_gather_kernel<long long><<<grid, 256, 0, stream>>>(g64, out_label_mask, nullptr, seg_len, pos_capacity, plist, cursor);
     else
-      pos_gather_kernel<uint8_t><<<grid, 256, 0, stream>>>(values, minmax, minmax_slot, gt_u8, out_label_mask, pos_u8, score_kind,
-                                                            seg_len, key_base, pos_capacity, plist, cursor);
+      pos_gather_kernel<uint8_t><<<grid, 256, 0, stream>>>(gt_u8, out_label_mask, pos_u8, seg_len, pos_capacity, plist, cursor);
     DML_LAUNCH_CHECK();
   }
   // 2. sort + distinct
@@ -627,7 +636,8 @@ int dml_ood_rank_segments(const float* values, const float* minmax, int32_t minm
     const size_t smem = (size_t)n2 * sizeof(uint32_t) + (size_t)(BUCKET_SORT_NB + 1) * sizeof(uint32_t) +
                         (size_t)BUCKET_SORT_MAX * sizeof(unsigned short) + 16;
     DML_CUDA_TRY(cudaFuncSetAttribute(pos_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    pos_sort_kernel<<<n_seg, RANK_THREADS, smem, stream>>>(plist, cursor, pos_capacity, key_base, S, pc, cnt, G, st);
+    pos_sort_kernel<<<n_seg, RANK_THREADS, smem, stream>>>(plist, cursor, pos_capacity, key_base, S, pc, cnt, G, st, values, minmax,
+                                                           minmax_slot, score_kind, seg_len);
     DML_LAUNCH_CHECK();
   }
   // 3. rank
