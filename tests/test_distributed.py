@@ -136,3 +136,56 @@ def test_choose_splitters_properties():
     assert b[0] == 0 and b[-1] == 1 << 32 and (b[1:] >= b[:-1]).all()
     assert all(int(v) % 2 == 0 for v in b[:-1])          # positive bit cleared: a score never straddles ranges
     assert choose_splitters(torch.tensor([-1, -1], dtype=torch.int64), 2).tolist() == [0, 0, 1 << 32]
+
+
+def _exchange_contract_worker(port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=0, world_size=1)
+    try:
+        from dml_b200 import distributed as D
+        ex = D.PositiveExchange("cpu", slot_keys=7, max_slots=2)          # capacity is rounded up to an even number of keys
+        out = {"slot_keys": ex.slot_keys, "stride": ex.stride, "errors": []}
+        run = torch.zeros(4, dtype=torch.int64)
+        for call in (lambda: ex.publish(run, 0),                          # publish without a slot
+                     lambda: ex.next_slot(9)):                            # a batch that may export more than a slot holds
+            try:
+                call()
+            except ValueError as e:
+                out["errors"].append(str(e))
+        keys, cnt = ex.next_slot(4)
+        keys[:3] = torch.tensor([5, 1, 9], dtype=torch.int32)
+        cnt[0] = 3
+        run[0] = 3
+        ex.publish(run, 100)
+        ex.publish_empty(run, 150)
+        try:
+            ex.next_slot(1)                                               # more batches than max_slots
+        except ValueError as e:
+            out["errors"].append(str(e))
+        rec = ex.finish()
+        hdr = rec[:, :, :D.PositiveExchange.HDR].contiguous().view(torch.int64)
+        out["hdr"] = hdr.tolist()
+        out["keys"] = rec[0, 0, D.PositiveExchange.HDR: D.PositiveExchange.HDR + 3].tolist()
+        ex.begin()
+        out["n_after_begin"] = ex.n
+        q.put(out)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_positive_exchange_contract():
+    """slot records, header layout and the error behaviour of distributed.PositiveExchange (one gloo rank)"""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    p = ctx.Process(target=_exchange_contract_worker, args=(_free_port(), q))
+    p.start()
+    out = q.get(timeout=120)
+    p.join(timeout=60)
+    assert p.exitcode == 0
+    assert out["slot_keys"] == 8 and out["stride"] == 12 + 8
+    assert len(out["errors"]) == 3 and "without next_slot" in out["errors"][0] and "slot capacity" in out["errors"][1] \
+        and "max_slots" in out["errors"][2]
+    # [slot][rank][(count, n_pos, n_nan, n_oow, -, keys so far)]
+    assert out["hdr"] == [[[3, 3, 0, 0, 0, 100]], [[0, 3, 0, 0, 0, 150]]]
+    assert out["keys"] == [5, 1, 9] and out["n_after_begin"] == 0

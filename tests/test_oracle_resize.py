@@ -55,3 +55,11 @@ def test_library_coefficient_tables_equal_the_oracle(sizes):
     np.testing.assert_array_equal(b, b_ref)
     np.testing.assert_array_equal(k, k_ref)
     assert lib.dml_resize_coeffs(n_in, n_out, b.ctypes.data_as(C.c_void_p), k.ctypes.data_as(C.c_void_p), ks + 1) != 0
+
+
+def test_product_target_sizes_equal_the_oracle():
+    from dml_b200.anomaly import dataset as D
+    for (h, w) in ((720, 1280), (1024, 2048), (90, 160), (375, 500), (500, 375)):
+        for sizes, mx, pad in (((300, 375, 450, 525, 600), 1000, 8), ((38, 47, 56, 66, 75), 125, 8), ((512,), 2048, 32)):
+            assert D.val_target_sizes(h, w, sizes, mx, pad) == R.val_target_sizes(h, w, sizes, mx, pad)
+    assert D.round2nearest_multiple(533, 8) == 536 and D.round2nearest_multiple(536, 8) == 536
