@@ -911,7 +911,7 @@ def run_ours(args):
             stages[-1]["exchanged_bytes_rank0"] = info.get("exchanged_bytes")
     stages.sort(key=lambda st: -st["share_of_step"])        # largest share of the step first
     roofline["stages"] = stages
-    roofline["traffic_source"] = "profiles/head_traffic.json (ncu dram__bytes of head_kernel, r1d capture; not re-measured in this run)"
+    roofline["traffic_source"] = "profiles/head_traffic.json (ncu dram__bytes of head_kernel at this launch shape, r2aj capture; not re-measured in this run)"
 
     # ---- results (also the parity self-check of the bench) ------------------------------------------
     vals, counts = pipe.ood.results_to_host(pipe.per_image, pipe.per_image_stats)
