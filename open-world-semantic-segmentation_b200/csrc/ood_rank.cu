@@ -67,6 +67,7 @@ __global__ void __launch_bounds__(256) pos_gather_kernel(const GT* __restrict__ 
   const long long stride = (long long)gridDim.x * blockDim.x;
   const long long q_end = ((nstep + stride - 1) / stride) * stride;   // block-uniform trip count (warp collectives below)
   uint32_t* out = plist + (size_t)seg * cap;
+  const uint32_t single4 = positive_label4(out_mask);
   for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < q_end; q += stride) {
     unsigned flags = 0u;
     const long long p0 = q * PER;
@@ -76,7 +77,7 @@ __global__ void __launch_bounds__(256) pos_gather_kernel(const GT* __restrict__ 
         const uint4 w1 = *reinterpret_cast<const uint4*>(gb + base + p0 + 16);
         const uint32_t ww[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
-        for (int j = 0; j < 8; ++j) flags |= byte_mask_to_bits(positive_bytes(ww[j], out_mask, pos_u8 != nullptr)) << (4 * j);
+        for (int j = 0; j < 8; ++j) flags |= byte_mask_to_bits(positive_bytes(ww[j], out_mask, pos_u8 != nullptr, single4)) << (4 * j);
       } else {
         for (int j = 0; j < PER; ++j) {
           const long long p = p0 + j;
@@ -301,6 +302,7 @@ __global__ void __launch_bounds__(RANK_THREADS, 1) rank_kernel(const float* __re
   const Norm nmm = load_norm(fz.msp ? minmax : nullptr, seg, 1);
   const bool fuse = fz.msp != nullptr;
   const bool overflow = seg_stats[(size_t)seg * 4 + 3] != 0ull;
+  const uint32_t single4 = positive_label4(out_mask);
   const int G = overflow ? 0 : (int)Gin[seg];
   const uint32_t* Sg = S + (size_t)seg * cap;
   uint32_t* gcnt = cnt + (size_t)seg * (2 * (size_t)cap + 2);
@@ -333,7 +335,7 @@ __global__ void __launch_bounds__(RANK_THREADS, 1) rank_kernel(const float* __re
         v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
         if (pos_u8 || sizeof(GT) == 1) {
           const uint32_t g = *reinterpret_cast<const uint32_t*>((pos_u8 ? pos_u8 : reinterpret_cast<const uint8_t*>(gt)) + i);
-          const uint32_t pm = positive_bytes(g, out_mask, pos_u8 != nullptr);
+          const uint32_t pm = positive_bytes(g, out_mask, pos_u8 != nullptr, single4);
 #pragma unroll
           for (int j = 0; j < 4; ++j) pos[j] = ((pm >> (8 * j)) & 1u) != 0u;
         } else {

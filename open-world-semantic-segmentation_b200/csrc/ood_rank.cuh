@@ -58,8 +58,17 @@ __device__ __forceinline__ float apply_norm(const Norm& n, float v) {
 
 // Positive flags of four ground-truth bytes at once: 0xFF in every byte of the result whose label is in `out_mask`
 // (labels 0..63) -- or, with `nonzero`, whose byte is non-zero (a positive mask).  One SIMD byte compare per set label.
-__device__ __forceinline__ uint32_t positive_bytes(uint32_t w, uint64_t out_mask, bool nonzero) {
+// `single4`: the label replicated into four bytes when out_mask holds exactly one label (the usual case: `seg_label == 13`),
+// else 0xffffffff -- computed once per kernel (positive_label4), so that the common case is ONE byte compare per word
+// instead of a 64-bit bit-scan loop (12 instructions per pixel in the gather kernel before).
+__device__ __forceinline__ uint32_t positive_label4(uint64_t out_mask) {
+  if (out_mask == 0ull || (out_mask & (out_mask - 1ull)) != 0ull) return 0xffffffffu;
+  const int l = __ffsll((long long)out_mask) - 1;          // < 64: never 0xff in a byte
+  return (uint32_t)l * 0x01010101u;
+}
+__device__ __forceinline__ uint32_t positive_bytes(uint32_t w, uint64_t out_mask, bool nonzero, uint32_t single4 = 0xffffffffu) {
   if (nonzero) return __vcmpne4(w, 0u);
+  if (single4 != 0xffffffffu) return __vcmpeq4(w, single4);
   uint32_t m = 0u;
   while (out_mask) {                       // warp-uniform: usually one label
     const int l = __ffsll((long long)out_mask) - 1;
