@@ -293,7 +293,7 @@ __global__ void __launch_bounds__(RANK_THREADS, 1) rank_kernel(const float* __re
                                                                const uint32_t* __restrict__ Gin, uint32_t* __restrict__ cnt) {
   extern __shared__ __align__(16) unsigned char s_raw[];
   uint32_t* s_S = reinterpret_cast<uint32_t*>(s_raw);                       // [pass_cap]
-  uint32_t* s_cnt = s_S + pass_cap;                                          // [2 * pass_cap + 2]
+  uint32_t* s_cnt = s_S + pass_cap + 1;                                      // [2 * pass_cap + 2] (after the sentinel slot)
   uint32_t* s_lut = s_cnt + 2 * pass_cap + 2;                                // [RANK_LUT]
   __shared__ unsigned s_c[2][RANK_THREADS / 32];
   const int seg = blockIdx.y, tid = threadIdx.x;
@@ -320,8 +320,10 @@ __global__ void __launch_bounds__(RANK_THREADS, 1) rank_kernel(const float* __re
     const bool last_pass = g0 + gn >= G;
     // ---- stage this pass's positives, zero its counters, build the index table ------------------------------
     for (int i = tid; i < gn; i += RANK_THREADS) s_S[i] = Sg[g0 + i];
+    if (tid == 0) s_S[gn] = 0xffffffffu;                                    // sentinel behind the last positive score
     for (int i = tid; i < 2 * gn + 2; i += RANK_THREADS) s_cnt[i] = 0u;
     const uint32_t s_prev = g0 > 0 ? Sg[g0 - 1] : 0u;
+    const bool one_pass = g0 == 0 && last_pass;                             // the usual case: no pass bookkeeping per pixel
     __syncthreads();
     SmemTable tab;
     tab.build(s_S, s_lut, gn, key_base);
@@ -411,14 +413,23 @@ __global__ void __launch_bounds__(RANK_THREADS, 1) rank_kernel(const float* __re
       }
 #pragma unroll
       for (int j = 0; j < VEC; ++j) lo[j] = tab.finish(sk[j], lo[j], hi[j]);
+      // (s_S[gn] holds 0xffffffff, which no 31-bit score key equals: no bound test on l)
+      if (one_pass) {
 #pragma unroll
-      for (int j = 0; j < VEC; ++j) {
-        const int l = lo[j];
-        const bool eq = l < gn && s_S[l] == sk[j];
-        // a negative belongs to the pass whose positives bracket it from above: (S[g0-1], S[g0+gn-1]] -- and to the
-        // last pass when it lies above every positive
-        const bool mine = (l > 0 || g0 == 0 || sk[j] > s_prev) && (l < gn || last_pass);
-        if (act[j] && mine) atomicAdd(&s_cnt[2 * l + (eq ? 1 : 0)], 1u);
+        for (int j = 0; j < VEC; ++j) {
+          const int l = lo[j];
+          if (act[j]) atomicAdd(&s_cnt[2 * l + (s_S[l] == sk[j] ? 1 : 0)], 1u);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+          const int l = lo[j];
+          const bool eq = s_S[l] == sk[j];
+          // a negative belongs to the pass whose positives bracket it from above: (S[g0-1], S[g0+gn-1]] -- and to the
+          // last pass when it lies above every positive
+          const bool mine = (l > 0 || g0 == 0 || sk[j] > s_prev) && (l < gn || last_pass);
+          if (act[j] && mine) atomicAdd(&s_cnt[2 * l + (eq ? 1 : 0)], 1u);
+        }
       }
     }
     __syncthreads();
@@ -647,7 +658,7 @@ int dml_ood_rank_segments(const float* values, const float* minmax, int32_t minm
     // positives of one pass: as many as fit next to their counters and the index table in 227 KB of shared memory
     int pass_cap = pos_capacity < 12288 ? pos_capacity : 12288;
     pass_cap = (pass_cap + 3) & ~3;
-    const size_t smem = (size_t)pass_cap * 4 + ((size_t)2 * pass_cap + 2) * 4 + SmemTable::lut_bytes() + 16;
+    const size_t smem = ((size_t)pass_cap + 1) * 4 + ((size_t)2 * pass_cap + 2) * 4 + SmemTable::lut_bytes() + 16;
     auto al = [](const void* q, size_t a) { return q == nullptr || (reinterpret_cast<uintptr_t>(q) % a) == 0; };
     const bool vec4 = (seg_len % 4 == 0) && al(values, 16) && al(keys_out, 16) && al(conf_out, 16) && al(msp, 16) &&
                       al(msp_norm_out, 16) && al(mix_out, 16) && al(gt_u8, 4) && al(pos_u8, 4);
