@@ -436,8 +436,8 @@ __global__ void __launch_bounds__(RANK_THREADS, 1) unit_rank_kernel(const uint32
   const Unit u = units[blockIdx.x];
   const long long g0 = (long long)u.bucket * cap_b;
   const int gn = (int)(min(g0 + cap_b, G) - g0);
-  uint32_t* s_S = s_mem;                                                        // [cap_b]
-  uint32_t* s_cnt = s_S + cap_b;                                                // [2 cap_b + 2]
+  uint32_t* s_S = s_mem;                                                        // [cap_b + 1]: sentinel behind the last score
+  uint32_t* s_cnt = s_S + cap_b + 1;                                            // [2 cap_b + 2]
   uint32_t* s_lut = s_cnt + 2 * cap_b + 2;
   const int tid = threadIdx.x;
   // The unit's chunks (slice, bucket) as ONE flat sequence of aligned 16-byte vectors: chunk j covers the vectors
@@ -455,6 +455,7 @@ __global__ void __launch_bounds__(RANK_THREADS, 1) unit_rank_kernel(const uint32
     s_vpre[j + 1] = len ? ((off + len + 3u) >> 2) - (off >> 2) : 0u;
   }
   for (int i = tid; i < gn; i += RANK_THREADS) s_S[i] = S[g0 + i];
+  if (tid == 0) s_S[gn] = 0xffffffffu;              // no 31-bit score key equals it: no bound test on l below
   for (int i = tid; i < 2 * gn + 2; i += RANK_THREADS) s_cnt[i] = 0u;
   __syncthreads();
   if (tid < 32) {                                   // warp 0: inclusive scan of the vector counts, 32 at a time
@@ -480,8 +481,7 @@ __global__ void __launch_bounds__(RANK_THREADS, 1) unit_rank_kernel(const uint32
     int lo, hi;
     tab.range(sk, lo, hi);
     const int l = tab.finish(sk, lo, hi);
-    const bool eq = l < gn && s_S[l] == sk;
-    atomicAdd(&s_cnt[2 * l + (eq ? 1 : 0)], 1u);
+    atomicAdd(&s_cnt[2 * l + (s_S[l] == sk ? 1 : 0)], 1u);
   };
   if constexpr (FLAT) {
     const uint32_t V = s_vpre[n_ch];
@@ -906,7 +906,7 @@ int dml_ood_bucket_rank(const uint32_t* keys, int64_t n, const uint32_t* group_s
   DML_LAUNCH_CHECK();
   bucket_scatter_kernel<<<(unsigned)p.n_slices, PT_THREADS, smem_s, stream>>>(keys, n, p.slice_len, U, p.B, key_base, rel, sbase, part);
   DML_LAUNCH_CHECK();
-  const size_t smem_u = (size_t)p.cap_b * 4 + ((size_t)2 * p.cap_b + 2) * 4 + SmemTable::lut_bytes() + 16;
+  const size_t smem_u = ((size_t)p.cap_b + 1) * 4 + ((size_t)2 * p.cap_b + 2) * 4 + SmemTable::lut_bytes() + 16;
   // chunk walk: flat (balanced for any chunk length) when the mean (slice, bucket) chunk is short, else long chunks by the
   // CTA + short ones per warp; DML_UNIT_RANK=flat|chunk overrides (A/B runs)
   bool flat = n / ((long long)p.n_slices * p.B) < PR_FLAT_BELOW;
