@@ -357,9 +357,9 @@ __global__ void __launch_bounds__(RANK_THREADS, 1) rank_kernel(const float* __re
       }
       uint32_t key[VEC];
       bool bad[VEC];
+      apply_norm_vec<VEC>(nm, v);
 #pragma unroll
       for (int j = 0; j < VEC; ++j) {
-        v[j] = apply_norm(nm, v[j]);
         unsigned c_nan = 0, c_oow = 0;
         key[j] = pack_key(v[j], kind, pos[j], key_base, c_nan, c_oow);
         bad[j] = c_nan != 0;
@@ -382,10 +382,11 @@ __global__ void __launch_bounds__(RANK_THREADS, 1) rank_kernel(const float* __re
             m[0] = fz.msp[i];
           }
 #pragma unroll
+          for (int j = 0; j < VEC; ++j) mn[j] = m[j];
+          apply_norm_vec<VEC>(nmm, mn);
+#pragma unroll
           for (int j = 0; j < VEC; ++j) {
-            mn[j] = apply_norm(nmm, m[j]);
             // NumPy: c = 1 / (1 + exp(lamda * (e - thre))); mix = c*e + (1-c)*mmsp   (float32)
-            // (1 / x correctly rounded == IEEE 1.0f / x: the reciprocal sequence is half the division subroutine)
             const float c = mix_coefficient_fast(v[j], fz.lambda, fz.thr);
             mx[j] = __fadd_rn(__fmul_rn(c, v[j]), __fmul_rn(__fsub_rn(1.0f, c), mn[j]));
           }

@@ -56,6 +56,30 @@ __device__ __forceinline__ float apply_norm(const Norm& n, float v) {
   return (q0 >= 1.0e-30f && n.r < 3.0e38f) ? q : __fdiv_rn(x, n.den);
 }
 
+// The same for the VEC values of a thread with ONE branch: the guard of apply_norm compiled to a compare + branch + reconvergence
+// pair per value (5 instructions x 8 sites per pixel quad in rank_kernel); the division fallback is taken only by the
+// pixel that sits on the segment's minimum.  Bit-identical to apply_norm element by element.
+template <int VEC>
+__device__ __forceinline__ void apply_norm_vec(const Norm& n, float (&v)[VEC]) {
+  if (!n.on) return;
+  float x[VEC], q0[VEC], q[VEC];
+  bool ok = n.r < 3.0e38f;
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) {
+    x[j] = __fsub_rn(v[j], n.lo);
+    q0[j] = __fmul_rn(x[j], n.r);
+    q[j] = __fmaf_rn(__fmaf_rn(-q0[j], n.den, x[j]), n.r, q0[j]);
+    ok = ok && (q0[j] >= 1.0e-30f);
+  }
+  if (ok) {
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) v[j] = q[j];
+  } else {
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) v[j] = (q0[j] >= 1.0e-30f && n.r < 3.0e38f) ? q[j] : __fdiv_rn(x[j], n.den);
+  }
+}
+
 // Positive flags of four ground-truth bytes at once: 0xFF in every byte of the result whose label is in `out_mask`
 // (labels 0..63) -- or, with `nonzero`, whose byte is non-zero (a positive mask).  One SIMD byte compare per set label.
 // `single4`: the label replicated into four bytes when out_mask holds exactly one label (the usual case: `seg_label == 13`),
