@@ -208,7 +208,8 @@ __global__ void __launch_bounds__(RANK_THREADS) bucket_count_kernel(const uint32
   const long long k0 = (long long)blockIdx.x * slice_len;
   const long long k1 = min(k0 + slice_len, n);
   auto visit = [&](uint32_t k) {
-    if (!(k & 1u)) atomicAdd(&s_c[bucket_of(tab, k >> 1, B)], 1u);
+    const int b = bucket_of(tab, k >> 1, B);      // for every key: only the atomic is conditional (predicated, no divergence region)
+    if (!(k & 1u)) atomicAdd(&s_c[b], 1u);
   };
   const bool aligned = (reinterpret_cast<uintptr_t>(keys + k0) & 15) == 0;   // slice_len is a multiple of 4
   const long long nvec = aligned && k1 > k0 ? (k1 - k0) / 4 : 0;
@@ -384,11 +385,13 @@ __global__ void __launch_bounds__(PT_THREADS, 2) bucket_scatter_kernel(const uin
     }
 #pragma unroll
     for (int j = 0; j < PT_ITEMS; ++j) {
-      br[j] = 0xffffffffu;
-      if (!(k[j] & 1u)) {
-        const int b = bucket_of(tab, k[j] >> 1, B);
-        br[j] = ((uint32_t)b << 16) | atomicAdd(&s_tc[b], 1u);      // rank inside (tile, bucket) < PT_TILE <= 65536
-      }
+      // the bucket is looked up for every key (1 % positives): only the atomic stays conditional, so the compiler predicates
+      // it instead of opening a divergence region around the whole search
+      const int b = bucket_of(tab, k[j] >> 1, B);
+      const bool neg = !(k[j] & 1u);
+      uint32_t r = 0u;
+      if (neg) r = atomicAdd(&s_tc[b], 1u);                         // rank inside (tile, bucket) < PT_TILE <= 65536
+      br[j] = neg ? (((uint32_t)b << 16) | r) : 0xffffffffu;
     }
     __syncthreads();
     // tile-local starts of the buckets; advance the running cursors
