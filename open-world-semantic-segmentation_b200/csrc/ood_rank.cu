@@ -419,7 +419,8 @@ __global__ void __launch_bounds__(RANK_THREADS, 1) rank_kernel(const float* __re
 #pragma unroll
         for (int j = 0; j < VEC; ++j) {
           const int l = lo[j];
-          if (act[j]) atomicAdd(&s_cnt[2 * l + (s_S[l] == sk[j] ? 1 : 0)], 1u);
+          const int slot = 2 * l + (s_S[l] == sk[j] ? 1 : 0);      // for every pixel: only the atomic is predicated
+          if (act[j]) atomicAdd(&s_cnt[slot], 1u);
         }
       } else {
 #pragma unroll
